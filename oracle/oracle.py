@@ -1,0 +1,176 @@
+"""ctypes binding of the CPU oracle (oracle/xr_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(xroute_env_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libxr_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "xr_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        p = C.c_void_p
+        i32p = C.POINTER(C.c_int32)
+        L.orc_create.restype = p
+        L.orc_create.argtypes = [C.c_int] * 3 + [i32p, i32p, C.POINTER(C.c_uint8), i32p, i32p] + [C.c_int] * 5
+        L.orc_destroy.argtypes = [p]
+        L.orc_load.restype = C.c_int
+        L.orc_load.argtypes = [p, C.c_int, i32p, C.c_int, i32p, i32p, i32p]
+        L.orc_reset.argtypes = [p]
+        L.orc_remaining.restype = C.c_int
+        L.orc_remaining.argtypes = [p, i32p]
+        L.orc_obs.restype = C.c_int
+        L.orc_obs.argtypes = [p, C.POINTER(C.c_float), C.c_int]
+        L.orc_export_nodes.argtypes = [p, i32p]
+        L.orc_step.restype = C.c_int
+        L.orc_step.argtypes = [p, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.orc_path_len.restype = C.c_int64
+        L.orc_path_len.argtypes = [p]
+        L.orc_conn_count.restype = C.c_int
+        L.orc_conn_count.argtypes = [p]
+        L.orc_get_path.argtypes = [p, i32p, i32p, C.POINTER(C.c_uint32)]
+        L.orc_settled.restype = C.c_int64
+        L.orc_settled.argtypes = [p]
+        L.orc_src_pin.restype = C.c_int
+        L.orc_src_pin.argtypes = [p, C.c_int]
+        L.orc_get_state.argtypes = [p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint16)]
+        L.orc_distance_field.restype = C.c_int
+        L.orc_distance_field.argtypes = [p, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint32)]
+        L.orc_reward.restype = C.c_double
+        L.orc_reward.argtypes = [C.c_int64] * 3
+        _lib = L
+    return _lib
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def reward(violation: int, wirelength: int, via: int) -> float:
+    return float(lib().orc_reward(int(violation), int(wirelength), int(via)))
+
+
+class OracleEnv:
+    """Single-region CPU environment with the oracle's route/commit/metrics/obs."""
+
+    def __init__(self, geom, inst=None):
+        L = lib()
+        self.geom = geom
+        xc, xcp = _i32(geom.x_coords)
+        yc, ycp = _i32(geom.y_coords)
+        ld = np.ascontiguousarray(geom.layer_dir, np.uint8)
+        pi, pip_ = _i32(geom.layer_pitch)
+        mw, mwp = _i32(geom.layer_min_width)
+        self._h = L.orc_create(geom.X, geom.Y, geom.Z, xcp, ycp, ld.ctypes.data_as(C.POINTER(C.c_uint8)),
+                               pip_, mwp, geom.via_cost, geom.grid_cost, geom.drc_cost,
+                               geom.fixed_shape_cost, geom.block_cost)
+        self.inst = None
+        if inst is not None:
+            self.load(inst)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def load(self, inst):
+        b, bp = _i32(inst.block_xyz.reshape(-1))
+        n, np_ = _i32(inst.ap_net)
+        p, pp = _i32(inst.ap_pin)
+        x, xp = _i32(inst.ap_xyz.reshape(-1))
+        rc = lib().orc_load(self._h, len(inst.block_xyz), bp, len(inst.ap_net), np_, pp, xp)
+        if rc != 0:
+            raise ValueError(f"orc_load failed: {rc}")
+        self.inst = inst
+        self.reset()
+
+    def reset(self):
+        lib().orc_reset(self._h)
+
+    def remaining(self) -> list[int]:
+        n = lib().orc_remaining(self._h, None)
+        out = np.zeros(max(n, 1), np.int32)
+        lib().orc_remaining(self._h, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return [int(v) for v in out[:n]]
+
+    def obs(self) -> np.ndarray:
+        """float32 [1, 2+7n, Z, Y, X] exactly as build_3Dgrid returns it."""
+        g = self.geom
+        n = len(self.remaining())
+        Cn = 2 + 7 * n
+        out = np.empty((Cn, g.cells), np.float32)
+        rc = lib().orc_obs(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), Cn)
+        assert rc == Cn, rc
+        return out.reshape(1, Cn, g.Z, g.Y, g.X)
+
+    def step(self, net: int, full: bool = False) -> dict:
+        out = np.zeros(10, np.int64)
+        rc = lib().orc_step(self._h, int(net), int(full), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        if rc != 0:
+            raise ValueError(f"orc_step({net}) failed: {rc}")
+        keys = ["d_violation", "d_wirelength", "d_via", "violation", "wirelength", "via",
+                "blocked", "shorted", "overflow", "done"]
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def last_paths(self):
+        """(cells int32 [n], conn_off int32 [k+1], conn_cost uint32 [k]) of the last step;
+        cells are canonical indices (z*Y + y)*X + x, target first."""
+        L = lib()
+        n = L.orc_path_len(self._h)
+        k = L.orc_conn_count(self._h)
+        cells = np.zeros(max(n, 1), np.int32)
+        off = np.zeros(k + 1, np.int32)
+        cost = np.zeros(max(k, 1), np.uint32)
+        L.orc_get_path(self._h, cells.ctypes.data_as(C.POINTER(C.c_int32)),
+                       off.ctypes.data_as(C.POINTER(C.c_int32)),
+                       cost.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return cells[:n], off, cost[:k]
+
+    def settled(self) -> int:
+        return int(lib().orc_settled(self._h))
+
+    def src_pin(self, net: int) -> int:
+        return int(lib().orc_src_pin(self._h, net))
+
+    def state(self):
+        g = self.geom
+        usage = np.zeros(g.cells, np.uint8)
+        owner = np.zeros(g.cells, np.uint16)
+        lib().orc_get_state(self._h, usage.ctypes.data_as(C.POINTER(C.c_uint8)),
+                            owner.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return usage.reshape(g.Z, g.Y, g.X), owner.reshape(g.Z, g.Y, g.X)
+
+    def distance_field(self, net: int, src_cells) -> np.ndarray:
+        g = self.geom
+        s, sp = _i32(src_cells)
+        out = np.zeros(g.cells, np.uint32)
+        rc = lib().orc_distance_field(self._h, int(net), sp, len(s), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert rc == 0
+        return out.reshape(g.Z, g.Y, g.X)
