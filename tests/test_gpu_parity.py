@@ -1,0 +1,194 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded instances -- paths, connection costs, occupancy state, metrics and observations
+must be BIT-EXACT (integer / index work; the float32 observation holds only 0/1 and
+small integers)."""
+import numpy as np
+import pytest
+
+from xroute_env_b200.instances import Geometry, ispd18_geometry, make_batch, make_instance
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_episode(geom, insts, seed=0, check_obs_every=1, steps=None, **vgkw):
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    vg = VecGame(geom, insts, device=0, **vgkw)
+    vg.reset()
+    oracles = [OracleEnv(geom, i) for i in insts]
+    rng = np.random.default_rng(seed)
+    orders = [list(rng.permutation(i.net_ids)) for i in insts]
+    for e, orc in enumerate(oracles):
+        assert np.array_equal(vg.obs_host(e).numpy(), orc.obs()), f"initial obs env {e}"
+        assert vg.legal_set(e) == set(orc.remaining())
+    T = max(len(o) for o in orders)
+    if steps is not None:
+        T = min(T, steps)
+    for t in range(T):
+        acts = np.array([int(o[t]) if t < len(o) else 0 for o in orders], np.int32)
+        vg.step(acts)
+        delta, done, cum = vg.results_host()
+        rew = vg.reward.cpu().numpy()
+        for e, orc in enumerate(oracles):
+            if acts[e] == 0:
+                assert [int(v) for v in delta[e]] == [0, 0, 0]
+                continue
+            m = orc.step(int(acts[e]))
+            oc, oo, ocost = orc.last_paths()
+            gc, go, gcost = vg.paths(e)
+            assert np.array_equal(ocost, gcost), (t, e, ocost, gcost)
+            assert np.array_equal(oo, go), (t, e)
+            assert np.array_equal(oc, gc), (t, e)
+            assert [int(v) for v in delta[e]] == [m["d_violation"], m["d_wirelength"], m["d_via"]], (t, e)
+            assert [int(v) for v in cum[e]] == [m["violation"], m["wirelength"], m["via"], m["blocked"],
+                                                 m["shorted"], m["overflow"]], (t, e)
+            assert int(done[e]) == m["done"]
+            assert rew[e] == -(500 * m["d_violation"] + 4 * m["d_via"] + 0.5 * m["d_wirelength"])
+            if t % check_obs_every == 0 or m["done"]:
+                assert np.array_equal(vg.obs_host(e).numpy(), orc.obs()), (t, e)
+                gu, go_ = vg.state(e)
+                ou, oo_ = orc.state()
+                assert np.array_equal(gu, ou) and np.array_equal(go_, oo_), (t, e)
+            assert vg.legal_set(e) == set(orc.remaining())
+    vg.close()
+
+
+@pytest.mark.parametrize("shape", [(25, 26, 9), (12, 10, 5), (40, 36, 9), (33, 31, 3), (64, 64, 2), (70, 9, 9)])
+def test_episode_small_grids(shape):
+    geom = ispd18_geometry(*shape)
+    insts = make_batch(geom, 6, 8, seed=100 + shape[0])
+    _run_episode(geom, insts, seed=shape[1])
+
+
+def test_episode_t1_7x7():
+    geom = ispd18_geometry(112, 116, 9)
+    insts = make_batch(geom, 4, 16, seed=5)
+    _run_episode(geom, insts, seed=1, check_obs_every=5)
+
+
+def test_episode_syn256_partial():
+    geom = ispd18_geometry(256, 256, 9)
+    insts = make_batch(geom, 2, 12, seed=11)
+    _run_episode(geom, insts, seed=2, check_obs_every=6, steps=12)
+
+
+def test_wide_grid_x300():
+    # X not a multiple of the warp tile: exercises padded rows / masked lanes
+    geom = ispd18_geometry(300, 40, 4)
+    insts = make_batch(geom, 2, 6, seed=21)
+    _run_episode(geom, insts, seed=3)
+
+
+def test_tall_grid_y600():
+    geom = ispd18_geometry(40, 600, 3)
+    insts = make_batch(geom, 2, 6, seed=22)
+    _run_episode(geom, insts, seed=4)
+
+
+def test_nonuniform_tracks():
+    rng = np.random.default_rng(9)
+    X, Y, Z = 45, 38, 6
+    geom = ispd18_geometry(X, Y, Z)
+    geom.x_coords = np.cumsum(rng.integers(100, 700, X)).astype(np.int32)
+    geom.y_coords = np.cumsum(rng.integers(100, 700, Y)).astype(np.int32)
+    insts = make_batch(geom, 4, 8, seed=31)
+    _run_episode(geom, insts, seed=5)
+
+
+def test_congested_many_pins():
+    # dense pins, heavy blockage: shorts / blocked cells / overflow become non-zero
+    geom = ispd18_geometry(30, 30, 3)
+    insts = make_batch(geom, 4, 24, seed=41, p_obstacle=0.35)
+    _run_episode(geom, insts, seed=6)
+
+
+def test_ragged_batch_and_idle_actions():
+    # environments with different numbers of nets: finished ones get action 0
+    geom = ispd18_geometry(32, 32, 4)
+    insts = [make_instance(geom, n, 50 + n) for n in (1, 3, 7, 5)]
+    _run_episode(geom, insts, seed=7)
+
+
+def test_illegal_action_leaves_state_unchanged():
+    from xroute_env_b200 import VecGame
+    from xroute_env_b200._lib import IllegalAction
+    geom = ispd18_geometry(25, 26, 9)
+    insts = make_batch(geom, 2, 4, seed=61)
+    vg = VecGame(geom, insts, device=0)
+    vg.reset()
+    before = vg.obs_host(0).clone()
+    with pytest.raises(IllegalAction):
+        vg.step(np.array([99, 1], np.int32))
+    vg.step(np.array([1, 1], np.int32))
+    with pytest.raises(IllegalAction):
+        vg.step(np.array([1, 2], np.int32))          # net 1 already routed in env 0
+    assert vg.legal_set(0) == {2, 3, 4}
+    vg.reset()
+    assert np.array_equal(vg.obs_host(0).numpy(), before.numpy())
+    vg.close()
+
+
+def test_reset_subset_and_second_episode():
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    geom = ispd18_geometry(28, 28, 9)
+    insts = make_batch(geom, 3, 5, seed=71)
+    vg = VecGame(geom, insts, device=0)
+    vg.reset()
+    oracles = [OracleEnv(geom, i) for i in insts]
+    for net in (2, 4):
+        vg.step(np.array([net] * 3, np.int32))
+        for o in oracles:
+            o.step(net)
+    vg.reset([1])
+    oracles[1].reset()
+    for e in range(3):
+        assert np.array_equal(vg.obs_host(e).numpy(), oracles[e].obs())
+    vg.step(np.array([1, 1, 1], np.int32))
+    delta, done, cum = vg.results_host()
+    for e in range(3):
+        m = oracles[e].step(1)
+        assert [int(v) for v in cum[e]][:3] == [m["violation"], m["wirelength"], m["via"]]
+        assert np.array_equal(vg.obs_host(e).numpy(), oracles[e].obs())
+    vg.close()
+
+
+def test_dlpack_views_alias_device_memory():
+    import torch
+    from xroute_env_b200 import VecGame
+    geom = ispd18_geometry(25, 26, 9)
+    insts = make_batch(geom, 3, 4, seed=81)
+    vg = VecGame(geom, insts, device=0)
+    vg.reset()
+    ob = vg.obs_batch()
+    assert ob.is_cuda and ob.dtype == torch.float32 and ob.shape == (3, 2 + 7 * 4, 9, 26, 25)
+    o1 = vg.obs(1)
+    assert o1.shape == (1, 30, 9, 26, 25) and o1.data_ptr() == ob[1].data_ptr()
+    assert torch.equal(o1.cpu(), vg.obs_host(1))
+    vg.step(np.array([1, 2, 3], np.int32))
+    assert vg.obs(1).shape == (1, 23, 9, 26, 25)
+    assert vg.n_remaining.cpu().tolist() == [3, 3, 3]
+    assert vg.legal.cpu()[1].tolist() == [0, 1, 0, 1, 1]
+    s = vg.stats().cpu()
+    assert s[0] == 3 and s[1] == 0
+    vg.close()
+
+
+def test_build_3dgrid_dropin_matches_oracle():
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import build_3Dgrid
+    from xroute_env_b200.instances import export_data
+    geom = ispd18_geometry(14, 12, 5)
+    inst = make_instance(geom, 6, 91)
+    orc = OracleEnv(geom, inst)
+    routed = set()
+    for net in (3, 5):
+        m = orc.step(net)
+        routed.add(net)
+    usage, _ = orc.state()
+    data = export_data(geom, inst, usage, (m["violation"], m["wirelength"], m["via"]))
+    obs, nets, v, w, a = build_3Dgrid(data, routed)
+    assert np.array_equal(obs.numpy(), orc.obs())
+    assert nets == set(orc.remaining()) and (v, w, a) == (m["violation"], m["wirelength"], m["via"])
+    obs2, nets2, *_ = build_3Dgrid(data, set(), bool_inference=True)
+    assert nets2 == set(inst.net_ids) and obs2.shape[1] == 2 + 7 * 6

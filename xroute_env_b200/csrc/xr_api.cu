@@ -1,0 +1,841 @@
+// xr_api.cu -- C ABI (include/xroute_b200.h) and host-side step state machine of the
+// B200-native XRoute environment hot path.  No torch types; CUDA runtime only.
+//
+// Host mirror of reference semantics:
+//   Game.reset  baseline/baseline_utils.py:441-481   -> xr_reset
+//   Game.step   baseline/baseline_utils.py:392-439   -> xr_step / xr_step_results
+//   legal set   baseline_utils.py:438,472            -> host mirror h_routed/h_has_ap
+#include "../../include/xroute_b200.h"
+#include "dlpack_abi.h"
+#include "xr_common.cuh"
+#include "xr_kernels_env.cuh"
+#include "xr_kernels_maze.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static std::string g_create_error;
+
+struct ProfEvent { int cls; cudaEvent_t a, b; };
+
+struct XrEnv {
+    XrConfig cfg;
+    Geo g;
+    Dev d;
+    int device = 0;
+    std::string err;
+    std::vector<void *> allocs;
+    // host copies of geometry
+    std::vector<int32_t> xc, yc;
+    // host mirrors
+    std::vector<uint8_t> h_routed, h_has_ap, h_done, h_loaded, h_reset;
+    std::vector<uint16_t> h_npins;      // distinct pins per net
+    std::vector<int32_t> h_nrem;
+    int32_t *p_act = nullptr;           // pinned [N][2]
+    int32_t *p_flags = nullptr;         // pinned [2]
+    int32_t *p_ids = nullptr;           // pinned [N]
+    int32_t *d_ids = nullptr;
+    int pumps_per_sync = 4;
+    // counters
+    long long n_launch = 0, n_sync = 0;
+    // profiling
+    bool prof = false;
+    std::vector<ProfEvent> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[XR_K_COUNT] = {0};
+    long long prof_n[XR_K_COUNT] = {0};
+    std::atomic<int> refs{1};           // handle + outstanding DLPack tensors
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            env->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            return XR_E_CUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+static int fail(XrEnv *env, int code, const std::string &msg) {
+    if (env) env->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <typename T>
+static cudaError_t dalloc(XrEnv *env, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+    env->allocs.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return e;
+}
+
+// -------------------------------------------------------------- launch helpers
+struct Launch {
+    XrEnv *env; int cls; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    Launch(XrEnv *e, int c, cudaStream_t s) : env(e), cls(c), st(s) {
+        env->n_launch++;
+        if (env->prof) {
+            a = get(); b = get();
+            cudaEventRecord(a, st);
+        }
+    }
+    cudaEvent_t get() {
+        if (!env->ev_pool.empty()) { cudaEvent_t e = env->ev_pool.back(); env->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ~Launch() {
+        if (env->prof) { cudaEventRecord(b, st); env->prof_pending.push_back({cls, a, b}); }
+    }
+};
+
+static void prof_collect(XrEnv *env) {
+    for (auto &p : env->prof_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(p.b);
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { env->prof_ms[p.cls] += ms; env->prof_n[p.cls]++; }
+        env->ev_pool.push_back(p.a); env->ev_pool.push_back(p.b);
+    }
+    env->prof_pending.clear();
+}
+
+// ----------------------------------------------------------------- create/destroy
+extern "C" int xr_version(void) { return XR_VERSION; }
+
+extern "C" const char *xr_last_error(const XrEnv *env) {
+    return env ? env->err.c_str() : g_create_error.c_str();
+}
+
+static void xr_free(XrEnv *env) {
+    cudaSetDevice(env->device);
+    for (void *p : env->allocs) cudaFree(p);
+    if (env->p_act) cudaFreeHost(env->p_act);
+    if (env->p_flags) cudaFreeHost(env->p_flags);
+    if (env->p_ids) cudaFreeHost(env->p_ids);
+    for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : env->ev_pool) cudaEventDestroy(e);
+    delete env;
+}
+static void xr_unref(XrEnv *env) {
+    if (env->refs.fetch_sub(1) == 1) xr_free(env);
+}
+
+extern "C" void xr_destroy(XrEnv *env) {
+    if (!env) return;
+    cudaSetDevice(env->device);
+    cudaDeviceSynchronize();
+    xr_unref(env);
+}
+
+extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
+    if (!cfg || !out) return fail(nullptr, XR_E_INVALID, "null argument");
+    if (cfg->n_envs < 1 || cfg->X < 2 || cfg->Y < 2 || cfg->Z < 1 || cfg->Z > XR_MAX_LAYERS ||
+        cfg->X > 1024 || cfg->Y > 1024 || cfg->max_nets < 1 || cfg->max_nets > 65535 || cfg->max_aps < 1)
+        return fail(nullptr, XR_E_INVALID, "grid/net limits: 2<=X,Y<=1024, 1<=Z<=16, 1<=max_nets<=65535");
+    if (!cfg->x_coords || !cfg->y_coords || !cfg->layer_dir || !cfg->layer_pitch || !cfg->layer_min_width)
+        return fail(nullptr, XR_E_INVALID, "geometry arrays missing");
+    if ((long long)cfg->X * cfg->Y * cfg->Z >= (1ll << 30))
+        return fail(nullptr, XR_E_INVALID, "grid too large");
+    cudaError_t ce = cudaSetDevice(cfg->device);
+    if (ce != cudaSuccess) return fail(nullptr, XR_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    XrEnv *env = new XrEnv();
+    env->cfg = *cfg;
+    env->device = cfg->device;
+    Geo &g = env->g;
+    memset(&g, 0, sizeof(g));
+    g.N = cfg->n_envs; g.X = cfg->X; g.Y = cfg->Y; g.Z = cfg->Z;
+    g.Xp = (cfg->X + 31) / 32 * 32;
+    g.cells = cfg->X * cfg->Y * cfg->Z;
+    g.cells_p = cfg->Z * cfg->Y * g.Xp;
+    g.cells_o = (g.cells + 15) / 16 * 16;
+    g.max_nets = cfg->max_nets; g.max_aps = cfg->max_aps;
+    g.obs_max_nets = (cfg->obs_max_nets < 0 || cfg->obs_max_nets > cfg->max_nets) ? cfg->max_nets : cfg->obs_max_nets;
+    g.path_cap = cfg->path_capacity > 0 ? cfg->path_capacity : 8 * (cfg->X + cfg->Y + cfg->Z) + 256;
+    g.conn_cap = 256;
+    const long long maxc = 2ll + 7ll * g.obs_max_nets;
+    g.obs_stride = (maxc * g.cells + 63) / 64 * 64;
+    env->pumps_per_sync = cfg->pumps_per_sync > 0 ? cfg->pumps_per_sync : 4;
+    env->xc.assign(cfg->x_coords, cfg->x_coords + cfg->X);
+    env->yc.assign(cfg->y_coords, cfg->y_coords + cfg->Y);
+    for (int i = 1; i < cfg->X; i++) if (env->xc[i] <= env->xc[i - 1]) { delete env; return fail(nullptr, XR_E_INVALID, "x_coords not increasing"); }
+    for (int i = 1; i < cfg->Y; i++) if (env->yc[i] <= env->yc[i - 1]) { delete env; return fail(nullptr, XR_E_INVALID, "y_coords not increasing"); }
+    g.uniform_x = 1; g.dx = env->xc[1] - env->xc[0];
+    for (int i = 1; i < cfg->X; i++) if (env->xc[i] - env->xc[i - 1] != g.dx) g.uniform_x = 0;
+    g.uniform_y = 1; g.dy = env->yc[1] - env->yc[0];
+    for (int i = 1; i < cfg->Y; i++) if (env->yc[i] - env->yc[i - 1] != g.dy) g.uniform_y = 0;
+    for (int z = 0; z < cfg->Z; z++) {
+        const int horiz = cfg->layer_dir[z] == 0;
+        for (int f = 0; f < 4; f++) {
+            const uint32_t base = 1u + (uint32_t)cfg->drc_cost * (f & 1) + (uint32_t)cfg->fixed_shape_cost * ((f >> 1) & 1);
+            g.multX[z][f] = base + (horiz ? 0u : (uint32_t)cfg->grid_cost);
+            g.multY[z][f] = base + (horiz ? (uint32_t)cfg->grid_cost : 0u);
+            g.multV[f] = base;
+        }
+        g.pen[z] = (uint32_t)cfg->block_cost * (uint32_t)cfg->layer_min_width[z] * 20u;
+        g.vlen[z] = (z + 1 < cfg->Z) ? (uint32_t)cfg->via_cost * (uint32_t)cfg->layer_pitch[z + 1] : 0u;
+    }
+    const size_t N = g.N;
+#define DA(ptr, n)                                                                        \
+    do {                                                                                  \
+        ce = dalloc(env, &(ptr), (size_t)(n));                                            \
+        if (ce != cudaSuccess) {                                                          \
+            std::string m = std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(ce); \
+            xr_free(env);                                                                 \
+            return fail(nullptr, XR_E_CUDA, m);                                           \
+        }                                                                                 \
+    } while (0)
+    Dev &d = env->d;
+    int32_t *dxc, *dyc;
+    DA(dxc, g.X); DA(dyc, g.Y);
+    cudaMemcpy(dxc, env->xc.data(), sizeof(int32_t) * g.X, cudaMemcpyHostToDevice);
+    cudaMemcpy(dyc, env->yc.data(), sizeof(int32_t) * g.Y, cudaMemcpyHostToDevice);
+    g.xc = dxc; g.yc = dyc;
+    DA(d.cellinfo, N * g.cells_p); DA(d.apnet, N * g.cells_p);
+    DA(d.ap_cellp, N * g.max_aps); DA(d.ap_obsoff, N * g.max_aps); DA(d.ap_pin, N * g.max_aps);
+    DA(d.ap_adj, N * g.max_aps); DA(d.net_start, N * (g.max_nets + 2)); DA(d.net_srcpin, N * (g.max_nets + 1));
+    DA(d.obst_obs, N * g.cells_o); DA(d.routed, N * (g.max_nets + 1)); DA(d.legal, N * (g.max_nets + 1));
+    DA(d.rank_net, N * g.max_nets); DA(d.n_remaining, N);
+    DA(d.dist, N * g.cells_p); DA(d.cflag, N * g.cells_p);
+    DA(d.act, N * 2); DA(d.phase, N); DA(d.changed, N); DA(d.reinit, N); DA(d.first, N);
+    DA(d.ap_conn, N * g.max_aps); DA(d.flags, 4);
+    DA(d.msum, N * 4); DA(d.delta, N * 3); DA(d.cum, N * 6); DA(d.wlvia, N * 2); DA(d.done, N);
+    DA(d.reward, N); DA(d.envstat, N * 8); DA(d.stats, XR_STATS_COUNT); DA(d.obs_do, N);
+    DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
+    DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
+    DA(env->d_ids, N);
+    {   // the observation block is the big one: do not memset it twice, but report OOM clearly
+        void *q = nullptr;
+        ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
+        if (ce != cudaSuccess) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "cudaMalloc observation buffer (%.2f GB): %s -- lower n_envs or obs_max_nets",
+                     (double)(sizeof(float) * N * (size_t)g.obs_stride) / 1e9, cudaGetErrorString(ce));
+            xr_free(env);
+            return fail(nullptr, XR_E_CUDA, buf);
+        }
+        env->allocs.push_back(q);
+        d.obs = reinterpret_cast<float *>(q);
+    }
+#undef DA
+    if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
+        cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
+        cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess) {
+        xr_free(env);
+        return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
+    }
+    env->h_routed.assign(N * (g.max_nets + 1), 0);
+    env->h_has_ap.assign(N * (g.max_nets + 1), 0);
+    env->h_npins.assign(N * (g.max_nets + 1), 0);
+    env->h_done.assign(N, 0); env->h_loaded.assign(N, 0); env->h_reset.assign(N, 0);
+    env->h_nrem.assign(N, 0);
+    // dynamic shared memory of the x+z sweep
+    const int smem = g.Z * g.Xp * 5;
+    cudaFuncSetAttribute(k_sweep_xz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_sweep_xz<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_sweep_xz<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_sweep_xz<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_sweep_xz<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_sweep_xz<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { std::string m = cudaGetErrorString(ce); xr_free(env); return fail(nullptr, XR_E_CUDA, m); }
+    *out = env;
+    return XR_OK;
+}
+
+// ------------------------------------------------------------------ load instance
+extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, const int32_t *block_xyz,
+                                int32_t n_ap, const int32_t *ap_net, const int32_t *ap_pin,
+                                const int32_t *ap_xyz) {
+    if (!env) return XR_E_INVALID;
+    const Geo &g = env->g;
+    if (env_id < 0 || env_id >= g.N) return fail(env, XR_E_INVALID, "env_id out of range");
+    if (n_ap > g.max_aps) return fail(env, XR_E_CAPACITY, "n_ap exceeds max_aps");
+    if (n_block < 0 || n_ap < 0 || (n_block && !block_xyz) || (n_ap && (!ap_net || !ap_pin || !ap_xyz)))
+        return fail(env, XR_E_INVALID, "bad instance arrays");
+    cudaSetDevice(env->device);
+    std::vector<uint32_t> ci((size_t)g.cells_p, 0);
+    std::vector<uint16_t> an((size_t)g.cells_p, 0);
+    for (int z = 0; z < g.Z; z++)
+        for (int y = 0; y < g.Y; y++)
+            for (int x = g.X; x < g.Xp; x++) ci[((size_t)z * g.Y + y) * g.Xp + x] = CI_PAD;
+    auto inb = [&](int x, int y, int z) { return x >= 0 && x < g.X && y >= 0 && y < g.Y && z >= 0 && z < g.Z; };
+    for (int i = 0; i < n_block; i++) {
+        const int x = block_xyz[3 * i], y = block_xyz[3 * i + 1], z = block_xyz[3 * i + 2];
+        if (!inb(x, y, z)) return fail(env, XR_E_INVALID, "blockage outside the grid");
+        ci[((size_t)z * g.Y + y) * g.Xp + x] |= CI_BLOCK;
+    }
+    // sort APs by (net, pin, input order) -- same canonical order as the oracle
+    std::vector<int> order(n_ap);
+    for (int i = 0; i < n_ap; i++) order[i] = i;
+    for (int i = 0; i < n_ap; i++) {
+        if (ap_net[i] < 1 || ap_net[i] > g.max_nets) return fail(env, XR_E_CAPACITY, "net id outside 1..max_nets");
+        if (ap_pin[i] < 1 || ap_pin[i] > 65535) return fail(env, XR_E_INVALID, "pin id outside 1..65535");
+        if (!inb(ap_xyz[3 * i], ap_xyz[3 * i + 1], ap_xyz[3 * i + 2])) return fail(env, XR_E_INVALID, "access point outside the grid");
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (ap_net[a] != ap_net[b]) return ap_net[a] < ap_net[b];
+        return ap_pin[a] < ap_pin[b];
+    });
+    std::vector<int32_t> cellp(g.max_aps, 0), obsoff(g.max_aps, 0), nstart(g.max_nets + 2, 0);
+    std::vector<uint16_t> pin(g.max_aps, 0), srcpin(g.max_nets + 1, 0);
+    std::vector<uint8_t> adj(g.max_aps, 0);
+    std::vector<int> sx(n_ap), sy(n_ap), sz(n_ap), snet(n_ap);
+    for (int k = 0; k < n_ap; k++) {
+        const int i = order[k];
+        const int x = ap_xyz[3 * i], y = ap_xyz[3 * i + 1], z = ap_xyz[3 * i + 2];
+        const size_t cp = ((size_t)z * g.Y + y) * g.Xp + x;
+        if (an[cp] != 0) return fail(env, XR_E_INVALID, "two access points share a cell");
+        if (ci[cp] & CI_BLOCK) return fail(env, XR_E_INVALID, "access point on a blockage");
+        an[cp] = (uint16_t)ap_net[i];
+        ci[cp] |= CI_ISAP;
+        cellp[k] = (int32_t)cp; obsoff[k] = (x * g.Y + y) * g.Z + z; pin[k] = (uint16_t)ap_pin[i];
+        sx[k] = x; sy[k] = y; sz[k] = z; snet[k] = ap_net[i];
+        nstart[ap_net[i] + 1]++;
+    }
+    for (int n = 1; n <= g.max_nets + 1; n++) nstart[n] += nstart[n - 1];
+    // adjacency flag (build_3Dgrid.py:126-138) and static source pin per net
+    static const int DXs[6] = {1, -1, 0, 0, 0, 0}, DYs[6] = {0, 0, 1, -1, 0, 0}, DZs[6] = {0, 0, 0, 0, 1, -1};
+    uint8_t *has_ap = &env->h_has_ap[(size_t)env_id * (g.max_nets + 1)];
+    uint16_t *npins = &env->h_npins[(size_t)env_id * (g.max_nets + 1)];
+    memset(has_ap, 0, g.max_nets + 1);
+    memset(npins, 0, sizeof(uint16_t) * (g.max_nets + 1));
+    for (int k = 0; k < n_ap; k++) {
+        for (int dir = 0; dir < 6; dir++) {
+            const int x = sx[k] + DXs[dir], y = sy[k] + DYs[dir], z = sz[k] + DZs[dir];
+            if (inb(x, y, z) && an[((size_t)z * g.Y + y) * g.Xp + x] == snet[k]) { adj[k] = 1; break; }
+        }
+    }
+    for (int net = 1; net <= g.max_nets; net++) {
+        const int s = nstart[net], t = nstart[net + 1];
+        if (s == t) continue;
+        has_ap[net] = 1;
+        int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1, np = 0;
+        for (int k = s; k < t; k++) {
+            xmin = std::min(xmin, sx[k]); xmax = std::max(xmax, sx[k]);
+            ymin = std::min(ymin, sy[k]); ymax = std::max(ymax, sy[k]);
+            if (k == s || pin[k] != pin[k - 1]) np++;
+        }
+        npins[net] = (uint16_t)std::min(np, 65535);
+        const int cx2 = xmin + xmax, cy2 = ymin + ymax;
+        long best = -1; int bp = 0;
+        for (int k = s; k < t; k++) {
+            const long sc = labs(2L * sx[k] - cx2) + labs(2L * sy[k] - cy2);
+            if (best < 0 || sc < best || (sc == best && pin[k] < bp)) { best = sc; bp = pin[k]; }
+        }
+        srcpin[net] = (uint16_t)bp;
+        if (np - 1 > g.conn_cap) return fail(env, XR_E_CAPACITY, "net has more than 257 pins");
+    }
+    const Dev &d = env->d;
+    const size_t e = env_id;
+    CK(cudaMemcpy(d.cellinfo + e * g.cells_p, ci.data(), sizeof(uint32_t) * g.cells_p, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.apnet + e * g.cells_p, an.data(), sizeof(uint16_t) * g.cells_p, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.ap_cellp + e * g.max_aps, cellp.data(), sizeof(int32_t) * g.max_aps, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.ap_obsoff + e * g.max_aps, obsoff.data(), sizeof(int32_t) * g.max_aps, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.ap_pin + e * g.max_aps, pin.data(), sizeof(uint16_t) * g.max_aps, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.ap_adj + e * g.max_aps, adj.data(), g.max_aps, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.net_start + e * (g.max_nets + 2), nstart.data(), sizeof(int32_t) * (g.max_nets + 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.net_srcpin + e * (g.max_nets + 1), srcpin.data(), sizeof(uint16_t) * (g.max_nets + 1), cudaMemcpyHostToDevice));
+    env->h_loaded[env_id] = 1;
+    env->h_reset[env_id] = 0;
+    return XR_OK;
+}
+
+// ------------------------------------------------------------------------ obs
+static int launch_obs(XrEnv *env, cudaStream_t st) {
+    const Geo &g = env->g;
+    int maxn = 0;
+    for (int i = 0; i < g.N; i++) maxn = std::max(maxn, std::min(env->h_nrem[i], g.obs_max_nets));
+    const long long total = (2ll + 7ll * maxn) * g.cells;
+    dim3 grid((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N);
+    {
+        Launch L(env, XR_K_OBS, st);
+        k_obs<<<grid, OBS_THREADS, 0, st>>>(env->g, env->d);
+    }
+    CK(cudaGetLastError());
+    return XR_OK;
+}
+
+static int grid_cells(const Geo &g, int per_thread) {
+    const int n = (g.cells_p / per_thread + 255) / 256;
+    return std::max(1, std::min(n, 4096));
+}
+
+// ---------------------------------------------------------------------- reset
+extern "C" int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *stream) {
+    if (!env) return XR_E_INVALID;
+    const Geo &g = env->g;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaSetDevice(env->device);
+    std::vector<int> ids;
+    if (env_ids == nullptr) { ids.resize(g.N); for (int i = 0; i < g.N; i++) ids[i] = i; }
+    else {
+        if (k < 0 || k > g.N) return fail(env, XR_E_INVALID, "bad env id count");
+        ids.assign(env_ids, env_ids + k);
+    }
+    for (int id : ids) {
+        if (id < 0 || id >= g.N) return fail(env, XR_E_INVALID, "env id out of range");
+        if (!env->h_loaded[id]) return fail(env, XR_E_STATE, "reset of an environment with no instance loaded");
+    }
+    const int nb = (g.N + 255) / 256;
+    if (env_ids == nullptr) {
+        Launch L(env, XR_K_MISC, st);
+        k_mark<<<nb, 256, 0, st>>>(env->g, env->d, 1);
+    } else {
+        { Launch L(env, XR_K_MISC, st); k_mark<<<nb, 256, 0, st>>>(env->g, env->d, 0); }
+        if (!ids.empty()) {
+            // p_ids is reused across calls: make sure the previous upload has been consumed
+            CK(cudaStreamSynchronize(st)); env->n_sync++;
+            memcpy(env->p_ids, ids.data(), sizeof(int32_t) * ids.size());
+            CK(cudaMemcpyAsync(env->d_ids, env->p_ids, sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice, st));
+            Launch L(env, XR_K_MISC, st);
+            k_mark_ids<<<((int)ids.size() + 255) / 256, 256, 0, st>>>(env->g, env->d, env->d_ids, (int)ids.size());
+        }
+    }
+    { Launch L(env, XR_K_MISC, st); k_reset_cells<<<dim3(grid_cells(g, 1), g.N), 256, 0, st>>>(env->g, env->d); }
+    { Launch L(env, XR_K_MISC, st); k_reset_env<<<nb, 256, 0, st>>>(env->g, env->d); }
+    CK(cudaGetLastError());
+    for (int id : ids) {
+        uint8_t *routed = &env->h_routed[(size_t)id * (g.max_nets + 1)];
+        const uint8_t *has_ap = &env->h_has_ap[(size_t)id * (g.max_nets + 1)];
+        memset(routed, 0, g.max_nets + 1);
+        int n = 0;
+        for (int net = 1; net <= g.max_nets; net++) n += has_ap[net];
+        env->h_nrem[id] = n;
+        env->h_done[id] = (n == 0);
+        env->h_reset[id] = 1;
+    }
+    return launch_obs(env, st);
+}
+
+// ----------------------------------------------------------------------- step
+template <int CPL>
+static void launch_xz(XrEnv *env, cudaStream_t st) {
+    const Geo &g = env->g;
+    Launch L(env, XR_K_SWEEP_XZ, st);
+    k_sweep_xz<CPL><<<dim3(g.Y, g.N), dim3(32, g.Z), (size_t)g.Z * g.Xp * 5, st>>>(env->g, env->d);
+}
+static void launch_sweep_xz(XrEnv *env, cudaStream_t st) {
+    const int cpl = (env->g.Xp + 31) / 32;
+    if (cpl <= 1) launch_xz<1>(env, st);
+    else if (cpl <= 2) launch_xz<2>(env, st);
+    else if (cpl <= 4) launch_xz<4>(env, st);
+    else if (cpl <= 8) launch_xz<8>(env, st);
+    else if (cpl <= 16) launch_xz<16>(env, st);
+    else launch_xz<32>(env, st);
+}
+template <int TH>
+static void launch_y(XrEnv *env, cudaStream_t st) {
+    const Geo &g = env->g;
+    Launch L(env, XR_K_SWEEP_Y, st);
+    k_sweep_y<TH><<<dim3(g.Xp / 32, g.Z, g.N), dim3(32, (g.Y + TH - 1) / TH), 0, st>>>(env->g, env->d);
+}
+static void launch_sweep_y(XrEnv *env, cudaStream_t st) {
+    const int Y = env->g.Y;
+    if (Y <= 128) launch_y<8>(env, st);
+    else if (Y <= 256) launch_y<16>(env, st);
+    else if (Y <= 512) launch_y<32>(env, st);
+    else launch_y<64>(env, st);
+}
+
+extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
+    if (!env || !actions) return XR_E_INVALID;
+    const Geo &g = env->g;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaSetDevice(env->device);
+    // ---- validate against the host mirror of the legal sets (state untouched on error)
+    bool any_route = false, any_act = false;
+    for (int i = 0; i < g.N; i++) {
+        const int a = actions[i];
+        if (a == 0) continue;
+        if (!env->h_reset[i]) return fail(env, XR_E_STATE, "step before reset");
+        if (a == -1) { any_act = true; continue; }
+        if (a < 1 || a > g.max_nets || !env->h_has_ap[(size_t)i * (g.max_nets + 1) + a] ||
+            env->h_routed[(size_t)i * (g.max_nets + 1) + a] || env->h_done[i]) {
+            char buf[128];
+            snprintf(buf, sizeof buf, "illegal action %d for environment %d", a, i);
+            return fail(env, XR_E_ILLEGAL, buf);
+        }
+        any_act = true;
+    }
+    // p_act is reused across calls: the previous step's upload must have completed
+    CK(cudaStreamSynchronize(st)); env->n_sync++;
+    for (int i = 0; i < g.N; i++) {
+        const int a = actions[i];
+        int route = 0;
+        if (a >= 1 && env->h_npins[(size_t)i * (g.max_nets + 1) + a] >= 2) { route = a; any_route = true; }
+        env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
+    }
+    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * 2 * g.N, cudaMemcpyHostToDevice, st));
+    if (any_route) {
+        Launch L(env, XR_K_ROUTE_BEGIN, st);
+        k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d);
+    }
+    { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
+    CK(cudaGetLastError());
+    if (any_route) {
+        long long pumps = 0;
+        const long long guard = 64ll * (g.X + g.Y + g.Z) + 4096;
+        for (;;) {
+            for (int p = 0; p < env->pumps_per_sync; p++) {
+                launch_sweep_xz(env, st);
+                launch_sweep_y(env, st);
+                { Launch L(env, XR_K_CONTROL, st); k_control<<<g.N, 32, 0, st>>>(env->g, env->d); }
+            }
+            pumps += env->pumps_per_sync;
+            CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st)); env->n_sync++;
+            if (env->p_flags[1] != 0) {
+                cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
+                return fail(env, XR_E_UNROUTABLE, "maze search failed (no path / inconsistent backtrace)");
+            }
+            if (env->p_flags[0] == 0) break;
+            if (pumps > guard * 64) return fail(env, XR_E_UNROUTABLE, "maze search did not converge");
+        }
+    }
+    if (any_act) {
+        { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d); }
+    }
+    { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d); }
+    CK(cudaGetLastError());
+    // ---- host mirror
+    for (int i = 0; i < g.N; i++) {
+        const int a = actions[i];
+        if (a >= 1) {
+            env->h_routed[(size_t)i * (g.max_nets + 1) + a] = 1;
+            env->h_nrem[i]--;
+            if (env->h_nrem[i] == 0) env->h_done[i] = 1;
+        } else if (a == -1) env->h_done[i] = 1;
+    }
+    if (any_act) return launch_obs(env, st);
+    return XR_OK;
+}
+
+extern "C" int xr_step_results(XrEnv *env, int32_t *delta, uint8_t *done, int64_t *cum, void *stream) {
+    if (!env) return XR_E_INVALID;
+    const Geo &g = env->g;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaSetDevice(env->device);
+    if (delta) CK(cudaMemcpyAsync(delta, env->d.delta, sizeof(int32_t) * 3 * g.N, cudaMemcpyDeviceToHost, st));
+    if (done) CK(cudaMemcpyAsync(done, env->d.done, g.N, cudaMemcpyDeviceToHost, st));
+    if (cum) CK(cudaMemcpyAsync(cum, env->d.cum, sizeof(int64_t) * XR_M_COUNT * g.N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); env->n_sync++;
+    return XR_OK;
+}
+
+// ------------------------------------------------------------------ obs access
+extern "C" int xr_obs_layout(const XrEnv *env, int64_t *obs_stride, int32_t *max_channels) {
+    if (!env) return XR_E_INVALID;
+    if (obs_stride) *obs_stride = env->g.obs_stride;
+    if (max_channels) *max_channels = 2 + 7 * env->g.obs_max_nets;
+    return XR_OK;
+}
+extern "C" int xr_obs_channels(const XrEnv *env, int32_t env_id, int32_t *channels) {
+    if (!env || env_id < 0 || env_id >= env->g.N || !channels) return XR_E_INVALID;
+    *channels = 2 + 7 * std::min(env->h_nrem[env_id], env->g.obs_max_nets);
+    return XR_OK;
+}
+extern "C" int xr_obs_copy(XrEnv *env, int32_t env_id, float *host_out, int64_t n_floats, void *stream) {
+    if (!env || env_id < 0 || env_id >= env->g.N || !host_out) return XR_E_INVALID;
+    const Geo &g = env->g;
+    const long long need = (2ll + 7ll * std::min(env->h_nrem[env_id], g.obs_max_nets)) * g.cells;
+    if (n_floats < need) return fail(env, XR_E_CAPACITY, "host observation buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaSetDevice(env->device);
+    CK(cudaMemcpyAsync(host_out, env->d.obs + (size_t)env_id * g.obs_stride, sizeof(float) * need, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); env->n_sync++;
+    return XR_OK;
+}
+
+struct DlCtx { XrEnv *env; int64_t shape[5]; int64_t strides[5]; };
+static void dl_deleter(XrDLManagedTensor *self) {
+    DlCtx *c = reinterpret_cast<DlCtx *>(self->manager_ctx);
+    xr_unref(c->env);
+    delete c;
+    delete self;
+}
+static XrDLManagedTensor *make_dl(XrEnv *env, void *data, int ndim, const int64_t *shape, const int64_t *strides,
+                                  uint8_t code, uint8_t bits) {
+    DlCtx *c = new DlCtx();
+    c->env = env;
+    for (int i = 0; i < ndim; i++) { c->shape[i] = shape[i]; c->strides[i] = strides[i]; }
+    XrDLManagedTensor *m = new XrDLManagedTensor();
+    m->dl_tensor.data = data;
+    m->dl_tensor.device.device_type = kXrDLCUDA; m->dl_tensor.device.device_id = env->device;
+    m->dl_tensor.ndim = ndim;
+    m->dl_tensor.dtype.code = code; m->dl_tensor.dtype.bits = bits; m->dl_tensor.dtype.lanes = 1;
+    m->dl_tensor.shape = c->shape; m->dl_tensor.strides = c->strides; m->dl_tensor.byte_offset = 0;
+    m->manager_ctx = c; m->deleter = dl_deleter;
+    env->refs.fetch_add(1);
+    return m;
+}
+
+extern "C" int xr_obs_dlpack(XrEnv *env, int32_t env_id, void **out) {
+    if (!env || !out || env_id < -1 || env_id >= env->g.N) return XR_E_INVALID;
+    const Geo &g = env->g;
+    const int64_t cells = g.cells;
+    if (env_id >= 0) {
+        const int64_t C = 2 + 7 * std::min(env->h_nrem[env_id], g.obs_max_nets);
+        const int64_t shape[5] = {1, C, g.Z, g.Y, g.X};
+        const int64_t strides[5] = {C * cells, cells, (int64_t)g.Y * g.X, g.X, 1};
+        *out = make_dl(env, env->d.obs + (size_t)env_id * g.obs_stride, 5, shape, strides, kXrDLFloat, 32);
+    } else {
+        const int64_t C = 2 + 7 * g.obs_max_nets;
+        const int64_t shape[5] = {g.N, C, g.Z, g.Y, g.X};
+        const int64_t strides[5] = {g.obs_stride, cells, (int64_t)g.Y * g.X, g.X, 1};
+        *out = make_dl(env, env->d.obs, 5, shape, strides, kXrDLFloat, 32);
+    }
+    return XR_OK;
+}
+
+static int buffer_info(XrEnv *env, int which, void **p, int *ndim, int64_t shape[2], uint8_t *code, uint8_t *bits) {
+    const Geo &g = env->g; const Dev &d = env->d;
+    shape[0] = g.N; shape[1] = 1; *ndim = 1;
+    switch (which) {
+    case XR_BUF_OBS: *p = d.obs; *ndim = 2; shape[1] = g.obs_stride; *code = kXrDLFloat; *bits = 32; break;
+    case XR_BUF_DELTA: *p = d.delta; *ndim = 2; shape[1] = 3; *code = kXrDLInt; *bits = 32; break;
+    case XR_BUF_CUM: *p = d.cum; *ndim = 2; shape[1] = XR_M_COUNT; *code = kXrDLInt; *bits = 64; break;
+    case XR_BUF_DONE: *p = d.done; *code = kXrDLUInt; *bits = 8; break;
+    case XR_BUF_NREMAIN: *p = d.n_remaining; *code = kXrDLInt; *bits = 32; break;
+    case XR_BUF_LEGAL: *p = d.legal; *ndim = 2; shape[1] = g.max_nets + 1; *code = kXrDLUInt; *bits = 8; break;
+    case XR_BUF_STATS: *p = d.stats; shape[0] = XR_STATS_COUNT; *code = kXrDLInt; *bits = 64; break;
+    case XR_BUF_REWARD: *p = d.reward; *code = kXrDLFloat; *bits = 64; break;
+    default: return XR_E_INVALID;
+    }
+    return XR_OK;
+}
+extern "C" int xr_buffer_dlpack(XrEnv *env, int32_t which, void **out) {
+    if (!env || !out) return XR_E_INVALID;
+    void *p; int ndim; int64_t shape[2]; uint8_t code, bits;
+    if (buffer_info(env, which, &p, &ndim, shape, &code, &bits) != XR_OK) return fail(env, XR_E_INVALID, "unknown buffer");
+    const int64_t strides[2] = {ndim == 2 ? shape[1] : 1, 1};
+    *out = make_dl(env, p, ndim, shape, strides, code, bits);
+    return XR_OK;
+}
+extern "C" int xr_buffer_ptr(XrEnv *env, int32_t which, void **dev_ptr, int64_t *n_bytes) {
+    if (!env || !dev_ptr) return XR_E_INVALID;
+    void *p; int ndim; int64_t shape[2]; uint8_t code, bits;
+    if (buffer_info(env, which, &p, &ndim, shape, &code, &bits) != XR_OK) return fail(env, XR_E_INVALID, "unknown buffer");
+    *dev_ptr = p;
+    if (n_bytes) *n_bytes = shape[0] * (ndim == 2 ? shape[1] : 1) * (bits / 8);
+    return XR_OK;
+}
+
+extern "C" int xr_legal_mask(const XrEnv *env, int32_t env_id, uint8_t *mask, int32_t *n_remaining) {
+    if (!env || env_id < 0 || env_id >= env->g.N) return XR_E_INVALID;
+    const Geo &g = env->g;
+    int n = 0;
+    for (int net = 0; net <= g.max_nets; net++) {
+        const bool rem = net >= 1 && env->h_has_ap[(size_t)env_id * (g.max_nets + 1) + net] &&
+                         !env->h_routed[(size_t)env_id * (g.max_nets + 1) + net] && !env->h_done[env_id];
+        if (mask) mask[net] = rem;
+        n += rem;
+    }
+    if (n_remaining) *n_remaining = n;
+    return XR_OK;
+}
+
+// ------------------------------------------------------------- parity exports
+extern "C" int xr_get_paths(XrEnv *env, int32_t env_id, int32_t *cells, int32_t cells_cap, int32_t *n_cells,
+                            int32_t *conn_off, uint32_t *conn_cost, int32_t conn_cap, int32_t *n_conn) {
+    if (!env || env_id < 0 || env_id >= env->g.N) return XR_E_INVALID;
+    const Geo &g = env->g; const Dev &d = env->d;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    int pn = 0, cn = 0;
+    CK(cudaMemcpy(&pn, d.path_n + env_id, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&cn, d.conn_n + env_id, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n_cells) *n_cells = pn;
+    if (n_conn) *n_conn = cn;
+    if (pn > g.path_cap || cn > g.conn_cap) return fail(env, XR_E_CAPACITY, "path record overflowed path_capacity");
+    if (cells) {
+        if (cells_cap < pn) return fail(env, XR_E_CAPACITY, "cells buffer too small");
+        CK(cudaMemcpy(cells, d.path + (size_t)env_id * g.path_cap, sizeof(int32_t) * pn, cudaMemcpyDeviceToHost));
+    }
+    if (conn_off && conn_cost) {
+        if (conn_cap < cn) return fail(env, XR_E_CAPACITY, "connection buffer too small");
+        CK(cudaMemcpy(conn_off, d.conn_off + (size_t)env_id * (g.conn_cap + 1), sizeof(int32_t) * (cn + 1), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(conn_cost, d.conn_cost + (size_t)env_id * g.conn_cap, sizeof(uint32_t) * cn, cudaMemcpyDeviceToHost));
+    }
+    return XR_OK;
+}
+
+extern "C" int xr_get_state(XrEnv *env, int32_t env_id, uint8_t *usage, uint16_t *owner) {
+    if (!env || env_id < 0 || env_id >= env->g.N) return XR_E_INVALID;
+    const Geo &g = env->g;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> ci((size_t)g.cells_p);
+    CK(cudaMemcpy(ci.data(), env->d.cellinfo + (size_t)env_id * g.cells_p, sizeof(uint32_t) * g.cells_p, cudaMemcpyDeviceToHost));
+    for (int z = 0; z < g.Z; z++)
+        for (int y = 0; y < g.Y; y++)
+            for (int x = 0; x < g.X; x++) {
+                const uint32_t c = ci[((size_t)z * g.Y + y) * g.Xp + x];
+                const size_t o = ((size_t)z * g.Y + y) * g.X + x;
+                if (usage) usage[o] = (uint8_t)((c & CI_USAGE_MASK) >> CI_USAGE_SHIFT);
+                if (owner) owner[o] = (uint16_t)(c & CI_OWNER_MASK);
+            }
+    return XR_OK;
+}
+
+extern "C" int xr_get_dist(XrEnv *env, int32_t env_id, uint32_t *dist) {
+    if (!env || env_id < 0 || env_id >= env->g.N || !dist) return XR_E_INVALID;
+    const Geo &g = env->g;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> dd((size_t)g.cells_p);
+    CK(cudaMemcpy(dd.data(), env->d.dist + (size_t)env_id * g.cells_p, sizeof(uint32_t) * g.cells_p, cudaMemcpyDeviceToHost));
+    for (int z = 0; z < g.Z; z++)
+        for (int y = 0; y < g.Y; y++)
+            for (int x = 0; x < g.X; x++)
+                dist[((size_t)z * g.Y + y) * g.X + x] = dd[((size_t)z * g.Y + y) * g.Xp + x];
+    return XR_OK;
+}
+
+// ---------------------------------------------------------------- stats / prof
+extern "C" int xr_stats_update(XrEnv *env, void *stream) {
+    if (!env) return XR_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaSetDevice(env->device);
+    { Launch L(env, XR_K_MISC, st); k_stats<<<1, 256, 0, st>>>(env->g, env->d); }
+    CK(cudaGetLastError());
+    return XR_OK;
+}
+
+extern "C" int xr_counters(const XrEnv *env, int64_t *kernel_launches, int64_t *relax_passes,
+                           int64_t *cells_relaxed, int64_t *host_syncs) {
+    if (!env) return XR_E_INVALID;
+    const Geo &g = env->g;
+    if (kernel_launches) *kernel_launches = env->n_launch;
+    if (host_syncs) *host_syncs = env->n_sync;
+    if (relax_passes || cells_relaxed) {
+        cudaSetDevice(env->device);
+        cudaDeviceSynchronize();
+        std::vector<long long> es((size_t)g.N * 8);
+        cudaMemcpy(es.data(), env->d.envstat, sizeof(long long) * 8 * g.N, cudaMemcpyDeviceToHost);
+        long long pumps = 0;
+        for (int i = 0; i < g.N; i++) pumps += es[8 * (size_t)i + 2];
+        if (relax_passes) *relax_passes = pumps * 2;
+        if (cells_relaxed) *cells_relaxed = pumps * 2 * (long long)g.cells;
+    }
+    return XR_OK;
+}
+
+extern "C" int xr_profile_enable(XrEnv *env, int32_t enable) {
+    if (!env) return XR_E_INVALID;
+    cudaSetDevice(env->device);
+    cudaDeviceSynchronize();
+    prof_collect(env);
+    env->prof = enable != 0;
+    return XR_OK;
+}
+extern "C" int xr_profile_get(XrEnv *env, double *ms, int64_t *launches) {
+    if (!env) return XR_E_INVALID;
+    cudaSetDevice(env->device);
+    cudaDeviceSynchronize();
+    prof_collect(env);
+    for (int k = 0; k < XR_K_COUNT; k++) {
+        if (ms) ms[k] = env->prof_ms[k];
+        if (launches) launches[k] = env->prof_n[k];
+        env->prof_ms[k] = 0; env->prof_n[k] = 0;
+    }
+    return XR_OK;
+}
+
+// ------------------------------------------- stand-alone build_3Dgrid replacement
+// Host side classifies the node stream exactly as getObstaclesAndAccessPoints
+// (baseline/build_3Dgrid.py:6-56); the tensor itself is produced by k_obs.
+extern "C" int xr_build_obs_from_nodes(int32_t device, int32_t X, int32_t Y, int32_t Z, int32_t n_nodes,
+                                       const int32_t *nodes, const uint8_t *keep_nets, int32_t max_net,
+                                       float *host_out, int64_t host_cap, int32_t *nets_out,
+                                       int32_t *n_nets_out, void *stream) {
+    if (X < 1 || Y < 1 || Z < 1 || n_nodes < 0 || (n_nodes && !nodes) || !host_out || max_net < 0)
+        return fail(nullptr, XR_E_INVALID, "bad argument");
+    if ((long long)X * Y * Z >= (1ll << 30)) return fail(nullptr, XR_E_INVALID, "grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return fail(nullptr, XR_E_CUDA, cudaGetErrorString(ce));
+    const int cells = X * Y * Z, cells_o = (cells + 15) / 16 * 16;
+    std::vector<uint8_t> ob(cells_o, 0);
+    std::vector<uint16_t> apnet(cells, 0);              // observation-layout index
+    std::vector<int> cnt(max_net + 2, 0);
+    auto off = [&](int x, int y, int z) { return (x * Y + y) * Z + z; };
+    int n_ap = 0;
+    for (int i = 0; i < n_nodes; i++) {
+        const int32_t *v = nodes + 6 * (size_t)i;
+        const int x = v[0], y = v[1], z = v[2], used = v[3], net = v[4];
+        if (x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z) return fail(nullptr, XR_E_INVALID, "node outside the grid");
+        if (net == -1) ob[off(x, y, z)] = 1;
+        else if (net == 0) { if (used == 1) ob[off(x, y, z)] = 1; }
+        else {
+            if (net < 1 || net > 65535) return fail(nullptr, XR_E_INVALID, "net id out of range");
+            if (used == 1) ob[off(x, y, z)] = 1;
+            if (net <= max_net && keep_nets && keep_nets[net]) {
+                if (apnet[off(x, y, z)] == 0) { cnt[net + 1]++; n_ap++; }
+                apnet[off(x, y, z)] = (uint16_t)net;
+            }
+        }
+    }
+    std::vector<int32_t> nets;
+    for (int net = 1; net <= max_net; net++) if (cnt[net + 1] > 0) nets.push_back(net);
+    const int n = (int)nets.size();
+    const long long total = (2ll + 7ll * n) * cells;
+    if (n_nets_out) *n_nets_out = n;
+    if (nets_out) for (int i = 0; i < n; i++) nets_out[i] = nets[i];
+    if (host_cap < total) return fail(nullptr, XR_E_CAPACITY, "host observation buffer too small");
+    // AP tables
+    std::vector<int32_t> nstart(max_net + 2, 0);
+    for (int k = 1; k <= max_net + 1; k++) nstart[k] = nstart[k - 1] + cnt[k];
+    std::vector<int32_t> fill(nstart), obsoff(std::max(n_ap, 1));
+    std::vector<uint8_t> adj(std::max(n_ap, 1), 0);
+    for (int x = 0; x < X; x++) for (int y = 0; y < Y; y++) for (int z = 0; z < Z; z++) {
+        const int o = off(x, y, z); const int net = apnet[o];
+        if (!net) continue;
+        const int k = fill[net]++;
+        obsoff[k] = o;
+        const bool a = (x + 1 < X && apnet[off(x + 1, y, z)] == net) || (x > 0 && apnet[off(x - 1, y, z)] == net) ||
+                       (y + 1 < Y && apnet[off(x, y + 1, z)] == net) || (y > 0 && apnet[off(x, y - 1, z)] == net) ||
+                       (z + 1 < Z && apnet[off(x, y, z + 1)] == net) || (z > 0 && apnet[off(x, y, z - 1)] == net);
+        adj[k] = a;
+    }
+    // one-environment device scratch
+    Geo g; memset(&g, 0, sizeof g);
+    g.N = 1; g.X = X; g.Y = Y; g.Z = Z; g.Xp = X; g.cells = cells; g.cells_p = cells; g.cells_o = cells_o;
+    g.max_nets = std::max(max_net, 1); g.max_aps = std::max(n_ap, 1); g.obs_max_nets = g.max_nets;
+    g.obs_stride = (total + 63) / 64 * 64;
+    Dev d; memset(&d, 0, sizeof d);
+    std::vector<void *> tmp;
+    auto A = [&](size_t bytes) -> void * { void *p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
+    auto freeall = [&]() { for (void *p : tmp) cudaFree(p); };
+    std::vector<int32_t> rank(g.max_nets, 0), ns2(g.max_nets + 2, 0);
+    for (int i = 0; i < n; i++) rank[i] = nets[i];
+    for (int k = 0; k <= max_net + 1 && k < g.max_nets + 2; k++) ns2[k] = nstart[k];
+    for (int k = max_net + 2; k < g.max_nets + 2; k++) ns2[k] = nstart[max_net + 1];
+    uint8_t one = 1;
+    d.obs = (float *)A(sizeof(float) * g.obs_stride);
+    d.obst_obs = (uint8_t *)A(cells_o); d.rank_net = (int32_t *)A(sizeof(int32_t) * g.max_nets);
+    d.n_remaining = (int32_t *)A(4); d.obs_do = (uint8_t *)A(1);
+    d.net_start = (int32_t *)A(sizeof(int32_t) * (g.max_nets + 2));
+    d.ap_obsoff = (int32_t *)A(sizeof(int32_t) * g.max_aps); d.ap_adj = (uint8_t *)A(g.max_aps);
+    if (!d.obs || !d.obst_obs || !d.rank_net || !d.n_remaining || !d.obs_do || !d.net_start || !d.ap_obsoff || !d.ap_adj) {
+        freeall(); return fail(nullptr, XR_E_CUDA, "cudaMalloc failed");
+    }
+    cudaMemcpyAsync(d.obst_obs, ob.data(), cells_o, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.rank_net, rank.data(), sizeof(int32_t) * g.max_nets, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.n_remaining, &n, 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.obs_do, &one, 1, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.net_start, ns2.data(), sizeof(int32_t) * (g.max_nets + 2), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.ap_obsoff, obsoff.data(), sizeof(int32_t) * g.max_aps, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.ap_adj, adj.data(), g.max_aps, cudaMemcpyHostToDevice, st);
+    k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), 1), OBS_THREADS, 0, st>>>(g, d);
+    cudaMemcpyAsync(host_out, d.obs, sizeof(float) * total, cudaMemcpyDeviceToHost, st);
+    ce = cudaStreamSynchronize(st);
+    freeall();
+    if (ce != cudaSuccess) return fail(nullptr, XR_E_CUDA, cudaGetErrorString(ce));
+    return XR_OK;
+}

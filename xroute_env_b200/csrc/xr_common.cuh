@@ -1,0 +1,104 @@
+// xr_common.cuh -- shared device/host definitions of the B200 XRoute hot path.
+//
+// Data layout in HBM (per environment e of a batch of N):
+//   router layout  : [Z][Y][Xp] x fastest, Xp = X rounded up to 32 (128-byte rows of
+//                    u32), padded index cp = (z*Y + y)*Xp + x
+//   observation    : float32 [C_max][cells], cell (x,y,z) at x*Y*Z + y*Z + z inside a
+//                    channel (the reshape-not-permute layout of
+//                    baseline/build_3Dgrid.py:97-103)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XR_INF 0x3FFFFFFFu
+#define XR_ZMAX 16
+
+// cellinfo bits
+#define CI_OWNER_MASK 0x0000FFFFu
+#define CI_USAGE_SHIFT 16
+#define CI_USAGE_MASK 0x00FF0000u
+#define CI_BLOCK 0x01000000u
+#define CI_PAD   0x02000000u
+#define CI_ISAP  0x04000000u
+#define CI_STATIC_MASK (CI_BLOCK | CI_PAD | CI_ISAP)
+
+// cflag bits (per-route scratch)
+#define CF_RS   1u   // another net's wire on the cell (route-shape cost)
+#define CF_FS   2u   // access point of another net (fixed-shape cost)
+#define CF_BLK  4u   // blockage
+#define CF_TREE 8u   // cell belongs to the tree of the net being routed
+
+struct Geo {
+    int N, X, Y, Z, Xp;
+    int cells;        // X*Y*Z
+    int cells_p;      // Z*Y*Xp
+    int cells_o;      // cells rounded up to 16 (stride of obst_obs)
+    int max_nets, max_aps, obs_max_nets, path_cap, conn_cap;
+    long long obs_stride;   // floats per environment
+    int uniform_x, uniform_y, dx, dy;
+    const int32_t *xc, *yc; // device copies of the track coordinates
+    uint32_t multX[XR_ZMAX][4];  // 1 + GRID*[layer not horizontal] + DRC*rs + FIXED*fs
+    uint32_t multY[XR_ZMAX][4];
+    uint32_t multV[4];
+    uint32_t pen[XR_ZMAX];       // BLOCKCOST * min_width[z] * 20
+    uint32_t vlen[XR_ZMAX];      // VIACOST * pitch[z+1]: via between z and z+1
+};
+
+struct Dev {
+    // static instance data
+    uint32_t *cellinfo;   // [N][cells_p]
+    uint16_t *apnet;      // [N][cells_p]
+    int32_t  *ap_cellp;   // [N][max_aps] padded router index
+    int32_t  *ap_obsoff;  // [N][max_aps] observation-layout offset
+    uint16_t *ap_pin;     // [N][max_aps]
+    uint8_t  *ap_adj;     // [N][max_aps] AP has a 6-neighbour AP of the same net
+    int32_t  *net_start;  // [N][max_nets+2]
+    uint16_t *net_srcpin; // [N][max_nets+1]
+    // dynamic environment state
+    uint8_t  *obst_obs;   // [N][cells_o] obstacle channel source, observation layout
+    uint8_t  *routed;     // [N][max_nets+1]
+    uint8_t  *legal;      // [N][max_nets+1]
+    int32_t  *rank_net;   // [N][max_nets] remaining net ids ascending
+    int32_t  *n_remaining;// [N]
+    // route state
+    uint32_t *dist;       // [N][cells_p]
+    uint8_t  *cflag;      // [N][cells_p]
+    int32_t  *act;        // [N][2] raw action, net to route (0 = none)
+    int32_t  *phase;      // [N] 0 idle, 1 routing
+    int32_t  *changed;    // [N]
+    int32_t  *reinit;     // [N]
+    int32_t  *first;      // [N]
+    uint8_t  *ap_conn;    // [N][max_aps]
+    int32_t  *flags;      // [0] number of envs routing, [1] error flag
+    // results
+    unsigned int *msum;   // [N][4] blocked, shorted, overflow
+    int32_t  *delta;      // [N][3]
+    long long *cum;       // [N][6]
+    long long *wlvia;     // [N][2] cumulative wirelength / via (commit time)
+    uint8_t  *done;       // [N]
+    double   *reward;     // [N]
+    long long *envstat;   // [N][8] steps, episodes, pumps, connections, sum dvio, sum dwl, sum dvia
+    long long *stats;     // [16]
+    uint8_t  *obs_do;     // [N]
+    float    *obs;        // [N][obs_stride]
+    // last routed paths (parity / debug)
+    int32_t  *path;       // [N][path_cap] canonical indices
+    int32_t  *path_n;     // [N]
+    int32_t  *conn_off;   // [N][conn_cap+1]
+    uint32_t *conn_cost;  // [N][conn_cap]
+    int32_t  *conn_n;     // [N]
+};
+
+__host__ __device__ inline uint32_t xr_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// weight of entering a cell with flags f along x / y on layer z, or through a via
+__device__ __forceinline__ uint32_t wgt_x(const Geo &g, int z, uint32_t len, uint32_t f) {
+    return len * g.multX[z][f & 3u] + ((f & CF_BLK) ? g.pen[z] : 0u);
+}
+__device__ __forceinline__ uint32_t wgt_y(const Geo &g, int z, uint32_t len, uint32_t f) {
+    return len * g.multY[z][f & 3u] + ((f & CF_BLK) ? g.pen[z] : 0u);
+}
+// via between layers zl and zl+1 entering layer zv
+__device__ __forceinline__ uint32_t wgt_v(const Geo &g, int zl, int zv, uint32_t f) {
+    return g.vlen[zl] * g.multV[f & 3u] + ((f & CF_BLK) ? g.pen[zv] : 0u);
+}

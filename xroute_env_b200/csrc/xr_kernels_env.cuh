@@ -1,0 +1,247 @@
+// xr_kernels_env.cuh -- observation build, congestion/reward reduction, reset and
+// per-step bookkeeping kernels (all HBM-bound, coalesced, 16-byte accesses).
+#pragma once
+#include "xr_common.cuh"
+
+// ------------------------------------------------------------------ observation
+// Replaces baseline/build_3Dgrid.py:94-188,224-270 (getObstacleGrid, getNetGrid,
+// getNetOrderChannel, _build_3Dgrid, the t.cat copy).  One pass: every CTA owns a
+// contiguous chunk of the environment's [2+7n][cells] float block, streams it out
+// with 16-byte stores (channel 0 from the obstacle bytes, channel 1 from the rank
+// list, net channels zero) and, after a block barrier, patches the access points
+// that fall inside its chunk.  Algorithmic bytes: 4*(2+7n)*cells written per env.
+#define OBS_THREADS 256
+#define OBS_F4_PER_THREAD 16
+#define OBS_CHUNK (OBS_THREADS * OBS_F4_PER_THREAD * 4)   // floats per CTA (64 KB)
+
+__device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d) {
+    const int env = blockIdx.y;
+    if (!d.obs_do[env]) return;
+    const int n_rem = d.n_remaining[env];
+    const int n = n_rem < g.obs_max_nets ? n_rem : g.obs_max_nets;
+    const long long cells = g.cells;
+    const long long total = (2ll + 7ll * n) * cells;
+    const long long lo = (long long)blockIdx.x * OBS_CHUNK;
+    if (lo >= total) return;
+    const long long hi = (lo + OBS_CHUNK < total) ? lo + OBS_CHUNK : total;
+    float *out = d.obs + (size_t)env * g.obs_stride;
+    const uint8_t *ob = d.obst_obs + (size_t)env * g.cells_o;
+    const int *rank = d.rank_net + (size_t)env * g.max_nets;
+    const long long special_end = 2 * cells;
+    // ---- stream the chunk
+#pragma unroll 4
+    for (int k = 0; k < OBS_F4_PER_THREAD; k++) {
+        const long long p = lo + ((long long)k * OBS_THREADS + threadIdx.x) * 4;
+        if (p >= hi) break;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < special_end) {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const long long q = p + j;
+                float val = 0.f;
+                if (q < cells) val = ob[q] ? 1.f : 0.f;
+                else if (q < special_end) { const long long idx = q - cells; val = idx < n_rem ? (float)rank[idx] : 0.f; }
+                e[j] = val;
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        st_stream_f4(out + p, v);
+    }
+    if (hi <= special_end || n == 0) return;
+    __syncthreads();
+    // ---- patch the access points of the net blocks that overlap [lo, hi)
+    const long long chlo = lo / cells, chhi = (hi - 1) / cells;
+    int r0 = chlo >= 2 ? (int)((chlo - 2) / 7) : 0;
+    int r1 = (int)((chhi - 2) / 7);
+    if (r1 > n - 1) r1 = n - 1;
+    const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
+    const size_t aoff = (size_t)env * g.max_aps;
+    for (int r = r0; r <= r1; r++) {
+        const int net = rank[r];
+        const long long base = (2ll + 7ll * r) * cells;
+        const int s = ns[net], t = ns[net + 1];
+        for (int i = s + threadIdx.x; i < t; i += OBS_THREADS) {
+            const long long p0 = base + d.ap_obsoff[aoff + i];
+            if (p0 >= lo && p0 < hi) out[p0] = 1.f;
+            if (d.ap_adj[aoff + i]) {
+#pragma unroll
+                for (int j = 1; j <= 6; j++) {
+                    const long long pj = p0 + j * cells;
+                    if (pj >= lo && pj < hi) out[pj] = 1.f;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------- metrics
+// Congestion reduction over the occupancy field (the "reward kernel"): blocked
+// cells (wire on a blockage), shorted cells (two nets on a cell, or a foreign wire
+// on a pin), overflow (sum of usage beyond capacity 1).  Stands in for the
+// simulator-side Request.reward_violation (net_ordering.proto:37).  Reads 4 bytes
+// per cell (cellinfo); apnet only for occupied AP cells.
+__global__ void __launch_bounds__(256) k_metrics(Geo g, Dev d) {
+    const int env = blockIdx.y;
+    if (d.act[2 * env] < 1) return;
+    const size_t eoff = (size_t)env * g.cells_p;
+    const uint4 *ci4 = reinterpret_cast<const uint4 *>(d.cellinfo + eoff);
+    const int n4 = g.cells_p >> 2;
+    unsigned blocked = 0, shorted = 0, overflow = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(ci4 + i);
+        const uint32_t c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t u = (c[k] & CI_USAGE_MASK) >> CI_USAGE_SHIFT;
+            if (u) {
+                blocked += (c[k] & CI_BLOCK) ? 1u : 0u;
+                bool sh = u >= 2u;
+                if (!sh && (c[k] & CI_ISAP)) sh = d.apnet[eoff + 4 * (size_t)i + k] != (c[k] & CI_OWNER_MASK);
+                shorted += sh ? 1u : 0u;
+                overflow += u - 1u;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        blocked += __shfl_xor_sync(0xFFFFFFFFu, blocked, off);
+        shorted += __shfl_xor_sync(0xFFFFFFFFu, shorted, off);
+        overflow += __shfl_xor_sync(0xFFFFFFFFu, overflow, off);
+    }
+    __shared__ unsigned sm[3][8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sm[0][w] = blocked; sm[1][w] = shorted; sm[2][w] = overflow; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned s = 0;
+        for (int k = 0; k < 8; k++) s += sm[threadIdx.x][k];
+        if (s) atomicAdd(&d.msum[4 * env + threadIdx.x], s);
+    }
+}
+
+// Rank list (remaining net ids ascending), legal mask, n_remaining of one env.
+__device__ void refresh_remaining(const Geo &g, const Dev &d, int env) {
+    // single thread: at most max_nets iterations
+    const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
+    const uint8_t *routed = d.routed + (size_t)env * (g.max_nets + 1);
+    uint8_t *legal = d.legal + (size_t)env * (g.max_nets + 1);
+    int *rank = d.rank_net + (size_t)env * g.max_nets;
+    int n = 0;
+    legal[0] = 0;
+    for (int k = 1; k <= g.max_nets; k++) {
+        const bool rem = !routed[k] && ns[k + 1] > ns[k];
+        legal[k] = rem;
+        if (rem) rank[n++] = k;
+    }
+    d.n_remaining[env] = n;
+}
+
+// Per-step epilogue (baseline_utils.py:426-438): metric deltas, done flag, reward
+// (train_PPO.py:101-102), remaining-net list for the order channel.
+__global__ void k_finalize(Geo g, Dev d) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= g.N) return;
+    const int raw = d.act[2 * env];
+    if (raw < 1) {
+        d.delta[3 * env] = 0; d.delta[3 * env + 1] = 0; d.delta[3 * env + 2] = 0;
+        d.reward[env] = 0.0;
+        return;
+    }
+    long long *cum = d.cum + 6 * (size_t)env;
+    const long long blocked = d.msum[4 * env], shorted = d.msum[4 * env + 1], overflow = d.msum[4 * env + 2];
+    d.msum[4 * env] = 0; d.msum[4 * env + 1] = 0; d.msum[4 * env + 2] = 0;
+    const long long vio = blocked + shorted, wl = d.wlvia[2 * env], via = d.wlvia[2 * env + 1];
+    const long long dv = vio - cum[0], dw = wl - cum[1], da = via - cum[2];
+    d.delta[3 * env] = (int)dv; d.delta[3 * env + 1] = (int)dw; d.delta[3 * env + 2] = (int)da;
+    cum[0] = vio; cum[1] = wl; cum[2] = via; cum[3] = blocked; cum[4] = shorted; cum[5] = overflow;
+    double r = -1.0;
+    r *= (double)dv * 500 + (double)da * 4 + (double)dw * 0.5;
+    d.reward[env] = r;
+    refresh_remaining(g, d, env);
+    const bool dn = d.n_remaining[env] == 0;
+    d.done[env] = dn;
+    long long *es = d.envstat + 8 * (size_t)env;
+    es[0] += 1;
+    if (dn) es[1] += 1;
+    es[4] += dv; es[5] += dw; es[6] += da;
+}
+
+// ------------------------------------------------------------------------ reset
+// Restore the environments flagged in obs_do to their loaded instance: clear
+// occupancy, rebuild the obstacle-channel bytes (transposing router -> observation
+// layout) and the per-env counters.  grid (chunks, N).
+__global__ void __launch_bounds__(256) k_reset_cells(Geo g, Dev d) {
+    const int env = blockIdx.y;
+    if (!d.obs_do[env]) return;
+    const size_t eoff = (size_t)env * g.cells_p;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.cells_p; i += stride)
+        d.cellinfo[eoff + i] &= CI_STATIC_MASK;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < g.cells; o += stride) {
+        const int z = o % g.Z, y = (o / g.Z) % g.Y, x = o / (g.Z * g.Y);
+        const uint32_t ci = d.cellinfo[eoff + ((size_t)z * g.Y + y) * g.Xp + x];
+        d.obst_obs[(size_t)env * g.cells_o + o] = (ci & CI_BLOCK) ? 1 : 0;
+    }
+}
+__global__ void k_reset_env(Geo g, Dev d) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= g.N || !d.obs_do[env]) return;
+    uint8_t *routed = d.routed + (size_t)env * (g.max_nets + 1);
+    for (int k = 0; k <= g.max_nets; k++) routed[k] = 0;
+    for (int k = 0; k < 6; k++) d.cum[6 * (size_t)env + k] = 0;
+    d.wlvia[2 * env] = 0; d.wlvia[2 * env + 1] = 0;
+    d.msum[4 * env] = 0; d.msum[4 * env + 1] = 0; d.msum[4 * env + 2] = 0;
+    d.delta[3 * env] = 0; d.delta[3 * env + 1] = 0; d.delta[3 * env + 2] = 0;
+    d.reward[env] = 0.0;
+    d.phase[env] = 0; d.path_n[env] = 0; d.conn_n[env] = 0;
+    refresh_remaining(g, d, env);
+    d.done[env] = d.n_remaining[env] == 0;
+}
+
+// Mark which environments a reset touches.  ids == nullptr: all.
+__global__ void k_mark(Geo g, Dev d, int value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < g.N) d.obs_do[i] = (uint8_t)value;
+}
+__global__ void k_mark_ids(Geo g, Dev d, const int *ids, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) d.obs_do[ids[i]] = 1;
+}
+
+// ------------------------------------------------------------------------ stats
+// Sum the per-environment counters into the int64 vector that is all-reduced
+// across GPUs (torch.distributed / NCCL, SUM).  One block.
+__global__ void __launch_bounds__(256) k_stats(Geo g, Dev d) {
+    long long acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0;
+    for (int e = threadIdx.x; e < g.N; e += blockDim.x) {
+        const long long *cum = d.cum + 6 * (size_t)e;
+        const long long *es = d.envstat + 8 * (size_t)e;
+        acc[0] += es[0]; acc[1] += es[1];
+        acc[2] += es[4]; acc[3] += es[5]; acc[4] += es[6];     // lifetime sums of the step deltas
+        acc[5] += cum[3]; acc[6] += cum[4]; acc[7] += cum[5];  // congestion snapshot of the running episodes
+        acc[8] += -(es[4] * 1000 + es[6] * 8 + es[5]);         // 2 * lifetime reward (exact integer)
+        acc[9] += es[2] * 2; acc[10] += es[2] * 2 * (long long)g.cells; acc[11] += es[3];
+    }
+    __shared__ long long sm[12][8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        long long v = acc[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        if (lane == 0) sm[k][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        long long s = 0;
+        if (threadIdx.x < 12) for (int k = 0; k < 8; k++) s += sm[threadIdx.x][k];
+        d.stats[threadIdx.x] = s;
+    }
+}
