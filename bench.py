@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the XRoute hot path (obs build + maze route + reward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): synthetic 256x256x9 grid, 64 environments per GPU,
+32 nets per environment, random net ordering, episodes back to back (reset every 32
+steps).  A "step" is one batched environment step: every environment of the batch
+routes one net, updates its metrics and rebuilds its observation.  Weak scaling: each
+rank owns its own 64-environment shard (seeded by global environment id), no data-path
+collective; the episode statistics vector is all-reduced once after the timed region.
+
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU oracle port of the
+same path on all host cores (the reference's own router is an absent external binary).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PRESET = "SYN-256"
+ENVS_PER_GPU = 64
+N_NETS = 32
+SEED = 20260000
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/xr_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], 0, set()
+        with open(self.path) as f:
+            for line in f:
+                c = [s.strip() for s in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx = max(mx, float(c[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     c[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_orders(insts, n_steps, seed):
+    """Per-environment action schedule: a fresh random permutation of the net ids per episode."""
+    rng = np.random.default_rng(seed)
+    n_eps = (n_steps + N_NETS - 1) // N_NETS + 1
+    sched = np.zeros((n_steps + N_NETS, len(insts)), np.int32)
+    for e, inst in enumerate(insts):
+        ids = np.array(inst.net_ids, np.int32)
+        assert len(ids) == N_NETS
+        seq = np.concatenate([rng.permutation(ids) for _ in range(n_eps)])
+        sched[:, e] = seq[: sched.shape[0]]
+    return sched
+
+
+# --------------------------------------------------------------------------- CPU side
+def _cpu_worker(args):
+    """One process = one environment at a time (how the reference runs), oracle port."""
+    first_env, n_envs, budget_s = args
+    import ctypes as C
+    from oracle.oracle import OracleEnv, lib
+    from xroute_env_b200.instances import make_instance, preset_geometry
+    geom = preset_geometry(PRESET)
+    buf = np.empty((2 + 7 * N_NETS, geom.cells), np.float32)
+    steps = routes = settled = 0
+    t0 = time.perf_counter()
+    for e in range(first_env, first_env + n_envs):
+        inst = make_instance(geom, N_NETS, SEED + e)
+        env = OracleEnv(geom, inst)
+        order = np.random.default_rng(SEED + e).permutation(inst.net_ids)
+        lib().orc_obs(env._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.shape[0])
+        for net in order:
+            env.step(int(net))
+            lib().orc_obs(env._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.shape[0])
+            steps += 1; routes += 1; settled += env.settled()
+            if time.perf_counter() - t0 > budget_s:
+                return steps, routes, settled, time.perf_counter() - t0
+    return steps, routes, settled, time.perf_counter() - t0
+
+
+def cpu_run(cores: int, budget_s: float):
+    """Oracle port on `cores` processes for about `budget_s` seconds.  Returns env-steps/s."""
+    if cores == 1:
+        res = [_cpu_worker((0, 4, budget_s))]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, [(4 * i, 4, budget_s) for i in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[3] for r in res)
+    return steps / wall, steps, sum(r[2] for r in res) / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    try:                                   # each worker holds a 0.53 GB observation buffer
+        import psutil
+        cores = max(1, min(cores, int(psutil.virtual_memory().available / 1.5e9)))
+    except Exception:
+        pass
+    per_step = []
+    total_steps = 0
+    # each "step" of this arm is a bounded sample: every core works for ~budget seconds
+    budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        v, steps, settled_s, wall = cpu_run(cores, budget)
+        if i >= args.warmup:
+            per_step.append((v, steps, wall, settled_s))
+            total_steps += steps
+    v = sum(p[1] for p in per_step) / sum(p[2] for p in per_step)
+    geom_dims = "256x256x9"
+    line = {
+        "impl": "reference", "metric": "env_steps_per_s", "value": v, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * statistics.mean(p[2] for p in per_step), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"SYN-256 {geom_dims}, {N_NETS} nets/env, random net order, obs+route+reward per env-step",
+                   "grid": geom_dims, "nets_per_env": N_NETS,
+                   "note": "CPU oracle port (oracle/xr_oracle.c), one environment per process on every host core; "
+                           "the reference's own router is an external binary that is not in its tree"},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{total_steps} env-steps in {len(per_step)} samples of ~{budget:.0f}s on {cores} processes"},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cells_settled_per_s": statistics.mean(p[3] for p in per_step),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU side
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from xroute_env_b200 import VecGame, make_batch, preset_geometry
+    from xroute_env_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    geom = preset_geometry(PRESET)
+    K, W = args.steps, args.warmup
+    insts = make_batch(geom, ENVS_PER_GPU, N_NETS, SEED, first_env=rank * ENVS_PER_GPU)
+    vg = VecGame(geom, insts, device=local)
+    total_steps = W + 3 * K + 5 * N_NETS
+    sched = make_orders(insts, total_steps, SEED + 17 * rank)
+    pinned = torch.from_numpy(sched).pin_memory()
+    sched_p = pinned.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = {"t": 0}
+
+    def one_step(read_results: bool):
+        t = state["t"]
+        if t % N_NETS == 0:
+            vg.reset()
+        vg.step(sched_p[t])
+        state["t"] = t + 1
+        if read_results:
+            delta, done, cum = vg.results_host()
+            return float(-(500.0 * delta[:, 0].sum() + 4.0 * delta[:, 2].sum() + 0.5 * delta[:, 1].sum()))
+        return None
+
+    def timed(n, read_results):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            one_step(read_results)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # warm-up (untimed)
+    for _ in range(W):
+        one_step(False)
+    # re-align to an episode boundary so every timed region sees the same mix of steps
+    while state["t"] % N_NETS != 0:
+        one_step(False)
+    base_t = state["t"]
+
+    sampler = ClockSampler(local)
+    c0 = vg.counters()
+    sampler.start()
+    ms_dev = timed(K, read_results=False)
+    clocks = sampler.stop()
+    c1 = vg.counters()
+    while state["t"] % N_NETS != 0:
+        one_step(False)
+    ms_e2e = timed(K, read_results=True)
+    while state["t"] % N_NETS != 0:
+        one_step(False)
+    # profiled leg: per-kernel-class CUDA-event timing on the launching stream
+    vg.profile(True)
+    t_prof0 = state["t"]
+    p0 = vg.counters()
+    ms_prof = timed(K, read_results=False)
+    prof = vg.profile_get()
+    vg.profile(False)
+    p1 = vg.counters()
+
+    env_steps = K * ENVS_PER_GPU * world
+    value = env_steps / (ms_dev / 1e3)
+    e2e = env_steps / (ms_e2e / 1e3)
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    cells_relaxed = c1["cells_relaxed"] - c0["cells_relaxed"]
+    relax_passes = c1["relax_passes"] - c0["relax_passes"]
+    if world > 1:
+        t = torch.tensor([cells_relaxed, relax_passes], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        cells_relaxed_all, relax_passes_all = float(t[0]), float(t[1])
+    else:
+        cells_relaxed_all, relax_passes_all = float(cells_relaxed), float(relax_passes)
+
+    # episode statistics: the only collective on this path (sum of a tiny int64 vector)
+    stats = vg.stats().clone()
+    if world > 1:
+        dist.all_reduce(stats)
+    stats = {k: int(v) for k, v in zip(_lib.STAT_NAMES, stats.cpu().tolist())}
+
+    # roofline of the dominant kernel class (rank 0, profiled leg)
+    peak, peak_src = _peaks()
+    cells = geom.cells
+    obs_bytes = 0.0
+    for t in range(t_prof0, t_prof0 + K):
+        n_rem_after = N_NETS - (t % N_NETS) - 1
+        obs_bytes += 4.0 * (2 + 7 * n_rem_after) * cells * ENVS_PER_GPU
+        if t % N_NETS == 0:
+            obs_bytes += 4.0 * (2 + 7 * N_NETS) * cells * ENVS_PER_GPU      # reset rebuilds the full obs
+    pumps_cells = (p1["cells_relaxed"] - p0["cells_relaxed"]) / 2.0          # cells per sweep kernel class
+    alg_bytes = {
+        "obs": obs_bytes,
+        "sweep_xz": 9.0 * pumps_cells,      # dist read+write (8 B) + flag byte
+        "sweep_y": 9.0 * pumps_cells,
+        "metrics": 4.0 * cells * ENVS_PER_GPU * K,
+        "route_begin": 11.0 * cells * ENVS_PER_GPU * K,
+    }
+    kern = {}
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    for k, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        ent = {"ms_total": round(v["ms"], 3), "launches": int(v["launches"]), "share": round(v["ms"] / tot_ms, 4),
+               "avg_us": round(1e3 * v["ms"] / v["launches"], 2)}
+        if k in alg_bytes and v["ms"] > 0:
+            ent["achieved_gbs"] = round(alg_bytes[k] / (v["ms"] / 1e3) / 1e9, 1)
+            ent["frac_of_hbm_peak"] = round(ent["achieved_gbs"] / peak, 4)
+        kern[k] = ent
+    dom = max((k for k in kern if k in alg_bytes), key=lambda k: kern[k]["ms_total"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(kern[dom]["achieved_gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dom] / kern[dom]["launches"],
+                "avg_launch_us": kern[dom]["avg_us"],
+                "note": "CUDA-event timing per kernel class in a profiled leg of the same K steps"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle
+        oracle.build()
+        v, steps, settled_s, wall = cpu_run(1, 15.0)
+        cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                        "sample": f"{steps} env-steps of the same workload (SYN-256, 32 nets) in {wall:.1f}s, "
+                                  "oracle/xr_oracle.c obs+route+reward, single thread",
+                        "cells_settled_per_s": settled_s}
+
+    if rank == 0:
+        h2d = ENVS_PER_GPU * 4
+        d2h = ENVS_PER_GPU * (3 * 4 + 1 + 6 * 8)
+        line = {
+            "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"SYN-256 256x256x9 grid, {ENVS_PER_GPU} envs/GPU, {N_NETS} nets/env, random net "
+                                   "order, back-to-back episodes (reset every 32 steps); obs+route+reward per env-step",
+                       "grid": "256x256x9", "envs_per_gpu": ENVS_PER_GPU, "nets_per_env": N_NETS,
+                       "l2": "working set (34 GB observations + 0.45 GB router state per GPU) >> 126 MB L2",
+                       "parallelism": f"env-shard x{world}"},
+            "net_routes_per_s": value,
+            "cells_relaxed_per_s": cells_relaxed_all / (ms_dev / 1e3),
+            "relax_passes_per_step": relax_passes_all / (K * world),
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K,
+                    "note": "xr_step with host actions + xr_step_results to pinned host (delta, done, cum); "
+                            "observations stay on the GPU (DLPack) by design"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kern,
+            "profiled_leg_ms_per_step": ms_prof / K,
+            "cpu_baseline": cpu_baseline,
+            "episode_stats": stats,
+        }
+        print(json.dumps(line), flush=True)
+    vg.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
