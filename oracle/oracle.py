@@ -59,6 +59,9 @@ def lib():
         L.orc_get_state.argtypes = [p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint16)]
         L.orc_distance_field.restype = C.c_int
         L.orc_distance_field.argtypes = [p, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint32)]
+        L.orc_set_usage.argtypes = [p, C.POINTER(C.c_uint8)]
+        L.orc_set_routed.restype = C.c_int
+        L.orc_set_routed.argtypes = [p, C.c_int, C.c_int]
         L.orc_reward.restype = C.c_double
         L.orc_reward.argtypes = [C.c_int64] * 3
         _lib = L
@@ -166,6 +169,14 @@ class OracleEnv:
         lib().orc_get_state(self._h, usage.ctypes.data_as(C.POINTER(C.c_uint8)),
                             owner.ctypes.data_as(C.POINTER(C.c_uint16)))
         return usage.reshape(g.Z, g.Y, g.X), owner.reshape(g.Z, g.Y, g.X)
+
+    def set_usage(self, usage: np.ndarray):
+        u = np.ascontiguousarray(usage, np.uint8).reshape(-1)
+        assert u.size == self.geom.cells
+        lib().orc_set_usage(self._h, u.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+    def set_routed(self, net: int, flag: bool = True):
+        lib().orc_set_routed(self._h, int(net), int(flag))
 
     def distance_field(self, net: int, src_cells) -> np.ndarray:
         g = self.geom

@@ -1,0 +1,82 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+from xroute_env_b200.instances import Instance, ispd18_geometry
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rows_to_oracle(rows, dims, routed=(), infer_netlist=None):
+    """Replay a golden node stream (rows of x,y,z,used,Net,Pin; tests/golden/make_golden.py)
+    through the CPU oracle: blockages / APs become the instance, `used` the occupancy."""
+    from oracle.oracle import OracleEnv
+    X, Y, Z = (int(v) for v in dims)
+    geom = ispd18_geometry(X, Y, Z)
+    blk = rows[rows[:, 4] == -1][:, :3]
+    ap = rows[rows[:, 4] >= 1]
+    inst = Instance(block_xyz=np.ascontiguousarray(blk, np.int32).reshape(-1, 3),
+                    ap_net=np.ascontiguousarray(ap[:, 4], np.int32),
+                    ap_pin=np.ascontiguousarray(ap[:, 5], np.int32),
+                    ap_xyz=np.ascontiguousarray(ap[:, :3], np.int32).reshape(-1, 3))
+    env = OracleEnv(geom, inst)
+    usage = np.zeros((Z, Y, X), np.uint8)
+    for x, y, z, used, net, pin in rows:
+        if used and net != -1:
+            usage[z, y, x] = 1
+    env.set_usage(usage)
+    nets = sorted(set(int(v) for v in ap[:, 4]))
+    if infer_netlist is not None:
+        for n in nets:
+            env.set_routed(n, n not in set(int(v) for v in infer_netlist))
+    else:
+        for n in routed:
+            if n in nets:
+                env.set_routed(int(n), True)
+    return env, geom, inst
+
+
+def rows_to_data(rows, dims, cum, netlist):
+    nodes = [[[int(r[0]), int(r[1]), int(r[2])], [0, 0, int(r[2])], [int(r[3]), int(r[4]), int(r[5])]] for r in rows]
+    return [[int(v) for v in dims], nodes, list(cum), [int(v) for v in netlist]]
+
+
+def golden_obs_cases():
+    z = np.load(os.path.join(GOLD, "obs_cases.npz"))
+    for i in range(int(z["n_cases"][0])):
+        k = f"c{i}"
+        yield dict(idx=i, dims=z[k + "_dims"], rows=z[k + "_rows"], infer=bool(z[k + "_mode"][0]),
+                   routed=[int(v) for v in z[k + "_routed"]], netlist=[int(v) for v in z[k + "_netlist"]],
+                   netset=[int(v) for v in z[k + "_netset"]], obs=z[k + "_obs"])
+
+
+def brute_force_dist(geom, cflag, sources):
+    """Independent restatement of the SPEC cost model as a dense
+    numpy Bellman-Ford over all six moves; cflag uint8 [Z,Y,X] bit0 rs, bit1 fs, bit2 blk."""
+    Z, Y, X = cflag.shape
+    INF = np.int64(1) << 40
+    rs, fs, blk = (cflag & 1).astype(np.int64), ((cflag >> 1) & 1).astype(np.int64), ((cflag >> 2) & 1).astype(np.int64)
+    base = 1 + geom.drc_cost * rs + geom.fixed_shape_cost * fs
+    pen = blk * (geom.block_cost * geom.layer_min_width.astype(np.int64)[:, None, None] * 20)
+    horiz = (geom.layer_dir == 0).astype(np.int64)[:, None, None]
+    multx = base + geom.grid_cost * (1 - horiz)
+    multy = base + geom.grid_cost * horiz
+    dx = np.diff(geom.x_coords.astype(np.int64))
+    dy = np.diff(geom.y_coords.astype(np.int64))
+    vlen = geom.via_cost * geom.layer_pitch.astype(np.int64)[1:]
+    d = np.full((Z, Y, X), INF, np.int64)
+    for (x, y, z) in sources:
+        d[z, y, x] = 0
+    while True:
+        nd = d.copy()
+        # +x: entering x from x-1 ; -x: entering x from x+1
+        nd[:, :, 1:] = np.minimum(nd[:, :, 1:], d[:, :, :-1] + dx[None, None, :] * multx[:, :, 1:] + pen[:, :, 1:])
+        nd[:, :, :-1] = np.minimum(nd[:, :, :-1], d[:, :, 1:] + dx[None, None, :] * multx[:, :, :-1] + pen[:, :, :-1])
+        nd[:, 1:, :] = np.minimum(nd[:, 1:, :], d[:, :-1, :] + dy[None, :, None] * multy[:, 1:, :] + pen[:, 1:, :])
+        nd[:, :-1, :] = np.minimum(nd[:, :-1, :], d[:, 1:, :] + dy[None, :, None] * multy[:, :-1, :] + pen[:, :-1, :])
+        nd[1:] = np.minimum(nd[1:], d[:-1] + vlen[:, None, None] * base[1:] + pen[1:])
+        nd[:-1] = np.minimum(nd[:-1], d[1:] + vlen[:, None, None] * base[:-1] + pen[:-1])
+        if np.array_equal(nd, d):
+            return d
+        d = nd

@@ -192,3 +192,40 @@ def test_build_3dgrid_dropin_matches_oracle():
     assert nets == set(orc.remaining()) and (v, w, a) == (m["violation"], m["wirelength"], m["via"])
     obs2, nets2, *_ = build_3Dgrid(data, set(), bool_inference=True)
     assert nets2 == set(inst.net_ids) and obs2.shape[1] == 2 + 7 * 6
+
+
+def test_build_3dgrid_dropin_matches_reference_golden():
+    """GPU build_3Dgrid drop-in against outputs of the reference's own build_3Dgrid."""
+    from helpers import golden_obs_cases, rows_to_data
+    from xroute_env_b200 import build_3Dgrid
+    n = 0
+    for c in golden_obs_cases():
+        data = rows_to_data(c["rows"], c["dims"], (3, 1010, 2), c["netlist"])
+        obs, nets, v, w, a = build_3Dgrid(data, set(c["routed"]), bool_inference=c["infer"])
+        assert np.array_equal(obs.numpy(), c["obs"]), c["idx"]
+        assert sorted(nets) == c["netset"] and (v, w, a) == (3, 1010, 2)
+        n += 1
+    assert n >= 20
+
+
+def test_game_dropin_episode_matches_oracle():
+    """The reference-compatible Game (reset/step signatures of baseline_utils.py:383-481)."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import Game
+    from xroute_env_b200.instances import Instance
+    geom = ispd18_geometry(25, 26, 9)
+    empty = Instance(block_xyz=np.zeros((0, 3), np.int32), ap_net=np.zeros(0, np.int32),
+                     ap_pin=np.zeros(0, np.int32), ap_xyz=np.zeros((0, 3), np.int32))
+    inst = make_instance(geom, 5, 77)
+    game = Game(geometry=geom, instances=[empty, inst])
+    obs, tries = game.reset()
+    assert tries == 1                                    # the empty region is skipped and counted
+    orc = OracleEnv(geom, inst)
+    assert obs.device.type == "cpu" and np.array_equal(obs.numpy(), orc.obs())
+    assert game.action_space == set(inst.net_ids)
+    for net in (3, 1, 5, 2, 4):
+        obs, done, vio, wl, via = game.step(net)
+        m = orc.step(net)
+        assert (vio, wl, via) == (m["d_violation"], m["d_wirelength"], m["d_via"]) and done == bool(m["done"])
+        assert np.array_equal(obs.numpy(), orc.obs()) and game.legal_action_set == set(orc.remaining())
+    assert done and obs.shape[1] == 2 and game.routed_nets == {1, 2, 3, 4, 5}

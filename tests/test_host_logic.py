@@ -1,0 +1,55 @@
+"""Host-side logic that needs no GPU: the seeded generator, the node-stream export and the
+shard arithmetic."""
+import numpy as np
+
+from xroute_env_b200.dist import shard_range
+from xroute_env_b200.instances import PRESETS, export_data, ispd18_geometry, make_batch, make_instance
+
+
+def test_generator_is_deterministic_and_valid():
+    g = ispd18_geometry(25, 26, 9)
+    a, b = make_instance(g, 12, 5), make_instance(g, 12, 5)
+    assert all(np.array_equal(getattr(a, f), getattr(b, f)) for f in ("block_xyz", "ap_net", "ap_pin", "ap_xyz"))
+    cells = set(map(tuple, a.ap_xyz.tolist()))
+    assert len(cells) == len(a.ap_xyz), "AP cells are distinct"
+    assert not cells & set(map(tuple, a.block_xyz.tolist())), "APs never sit on blockages"
+    assert a.net_ids == list(range(1, 13))
+    for n in a.net_ids:
+        assert len(set(a.ap_pin[a.ap_net == n].tolist())) >= 2
+    assert (a.ap_xyz[:, 2] <= 1).all()
+
+
+def test_batch_shards_compose():
+    g = ispd18_geometry(16, 16, 3)
+    whole = make_batch(g, 6, 4, seed=9)
+    lo = make_batch(g, 3, 4, seed=9, first_env=0)
+    hi = make_batch(g, 3, 4, seed=9, first_env=3)
+    for w, s in zip(whole, lo + hi):
+        assert np.array_equal(w.ap_xyz, s.ap_xyz) and np.array_equal(w.block_xyz, s.block_xyz)
+
+
+def test_shard_range_partitions():
+    for total, world in ((4096, 8), (10, 4), (3, 8), (64, 1)):
+        got = []
+        for r in range(world):
+            f, c = shard_range(total, r, world)
+            got += list(range(f, f + c))
+        assert got == list(range(total))
+
+
+def test_export_data_layout():
+    g = ispd18_geometry(5, 4, 3)
+    inst = make_instance(g, 2, 1)
+    usage = np.zeros((3, 4, 5), np.uint8)
+    x, y, z = (int(v) for v in inst.ap_xyz[0])
+    usage[z, y, x] = 1
+    data = export_data(g, inst, usage, (1, 2, 3))
+    assert data[0] == [5, 4, 3] and data[2] == [1, 2, 3] and data[3] == [1, 2] and len(data[1]) == 60
+    node = [n for n in data[1] if n[0] == [x, y, z]][0]
+    assert node[2] == [1, int(inst.ap_net[0]), int(inst.ap_pin[0])] and node[1][:2] == [200 + 400 * x, 190 + 380 * y]
+    blk = [n for n in data[1] if n[2][1] == -1]
+    assert len(blk) == len(inst.block_xyz) and all(n[2][0] == 1 for n in blk)
+
+
+def test_presets():
+    assert PRESETS["T1-7x7"] == (112, 116, 9) and PRESETS["SYN-256"] == (256, 256, 9)

@@ -1,0 +1,148 @@
+"""The maze part of the oracle has no reference vectors (PARITY UNPINNED, see
+oracle/xr_oracle.c header); it is checked here against (a) hand-made mazes with known
+answers and (b) an independent dense numpy Bellman-Ford restatement of the SPEC."""
+import numpy as np
+import pytest
+
+from helpers import brute_force_dist
+from oracle.oracle import OracleEnv
+from xroute_env_b200.instances import Instance, ispd18_geometry, make_instance
+
+
+def _inst(block, aps):
+    return Instance(block_xyz=np.array(block, np.int32).reshape(-1, 3),
+                    ap_net=np.array([a[0] for a in aps], np.int32), ap_pin=np.array([a[1] for a in aps], np.int32),
+                    ap_xyz=np.array([a[2] for a in aps], np.int32).reshape(-1, 3))
+
+
+def ci(g, x, y, z):
+    return (z * g.Y + y) * g.X + x
+
+
+def test_straight_preferred_direction():
+    g = ispd18_geometry(10, 6, 3)                       # layer 0 horizontal
+    env = OracleEnv(g, _inst([], [(1, 1, (1, 2, 0)), (1, 2, (7, 2, 0))]))
+    m = env.step(1)
+    cells, off, cost = env.last_paths()
+    assert cost.tolist() == [6 * 400] and m["d_wirelength"] == 2400 and m["d_via"] == 0 and m["d_violation"] == 0
+    assert len(cells) == 7 and all(c == ci(g, x, 2, 0) for c, x in zip(cells, range(7, 0, -1))) or \
+        all(c == ci(g, x, 2, 0) for c, x in zip(cells, range(1, 8)))
+
+
+def test_wrong_way_uses_upper_layer_when_cheaper():
+    g = ispd18_geometry(6, 12, 3)                       # y move on layer 0 costs 3x; layer 1 is vertical
+    env = OracleEnv(g, _inst([], [(1, 1, (2, 1, 0)), (1, 2, (2, 10, 0))]))
+    m = env.step(1)
+    _, _, cost = env.last_paths()
+    wrong_way = 9 * 380 * 3
+    via_route = 2 * 4 * 400 + 9 * 380
+    assert cost[0] == min(wrong_way, via_route) == via_route
+    assert m["d_via"] == 2 and m["d_wirelength"] == 9 * 380
+
+
+def test_blockage_is_detoured_not_crossed():
+    g = ispd18_geometry(9, 5, 1)
+    block = [(4, y, 0) for y in range(0, 4)]            # wall with a gap at y = 4
+    env = OracleEnv(g, _inst(block, [(1, 1, (1, 1, 0)), (1, 2, (7, 1, 0))]))
+    m = env.step(1)
+    cells, _, cost = env.last_paths()
+    assert m["blocked"] == 0 and m["d_violation"] == 0
+    detour = 6 * 400 + 2 * 3 * 380 * 3                  # 6 x-steps + 3 up + 3 down wrong-way on a horizontal layer
+    assert cost[0] == detour
+    assert ci(g, 4, 4, 0) in set(cells.tolist())
+
+
+def test_short_through_other_net_counts_violation():
+    g = ispd18_geometry(7, 3, 1)
+    # net 1 builds a vertical wall x=3 (wrong-way, only layer); net 2 must cross it
+    aps = [(1, 1, (3, 0, 0)), (1, 2, (3, 2, 0)), (2, 1, (0, 1, 0)), (2, 2, (6, 1, 0))]
+    env = OracleEnv(g, _inst([], aps))
+    m1 = env.step(1)
+    assert m1["d_violation"] == 0
+    m2 = env.step(2)
+    assert m2["shorted"] == 1 and m2["overflow"] == 1 and m2["d_violation"] == 1 and m2["done"] == 1
+    _, _, cost = env.last_paths()
+    assert cost[0] == 5 * 400 + 400 * (1 + 8)            # one cell at drc cost 8
+
+
+def test_multi_pin_tree_and_source_pin():
+    g = ispd18_geometry(11, 11, 2)
+    aps = [(1, 1, (0, 5, 0)), (1, 2, (5, 5, 0)), (1, 3, (10, 5, 0)), (1, 4, (5, 0, 1))]
+    env = OracleEnv(g, _inst([], aps))
+    assert env.src_pin(1) == 2                          # the pin at the bbox centre
+    m = env.step(1)
+    cells, off, cost = env.last_paths()
+    assert len(cost) == 3 and m["done"] == 1
+    assert sorted(cost.tolist()) == sorted([2000, 2000, 4 * 400 + 5 * 380])
+    usage, owner = env.state()
+    assert usage.sum() == len(set(cells.tolist())) and (owner[usage > 0] == 1).all()
+
+
+def test_tie_break_is_canonical():
+    g = ispd18_geometry(5, 5, 1)
+    # two targets at equal distance: the smaller cell index wins
+    aps = [(1, 1, (2, 2, 0)), (1, 2, (0, 2, 0)), (1, 3, (4, 2, 0))]
+    env = OracleEnv(g, _inst([], aps))
+    env.step(1)
+    cells, off, cost = env.last_paths()
+    assert cost.tolist() == [800, 800]
+    assert cells[off[0]] == ci(g, 0, 2, 0) and cells[off[1]] == ci(g, 4, 2, 0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_distance_field_matches_brute_force(seed):
+    rng = np.random.default_rng(seed)
+    X, Y, Z = int(rng.integers(4, 14)), int(rng.integers(4, 14)), int(rng.integers(1, 6))
+    g = ispd18_geometry(X, Y, Z)
+    if seed % 2:
+        g.x_coords = np.cumsum(rng.integers(50, 900, X)).astype(np.int32)
+        g.y_coords = np.cumsum(rng.integers(50, 900, Y)).astype(np.int32)
+    inst = make_instance(g, 5, seed, p_obstacle=0.3)
+    env = OracleEnv(g, inst)
+    order = [int(v) for v in rng.permutation(inst.net_ids)]
+    for net in order[:3]:
+        env.step(net)
+    net = order[3]
+    usage, _ = env.state()
+    apnet = np.zeros((Z, Y, X), np.int64)
+    for n, (x, y, z) in zip(inst.ap_net, inst.ap_xyz):
+        apnet[z, y, x] = n
+    blk = np.zeros((Z, Y, X), np.uint8)
+    for x, y, z in inst.block_xyz:
+        blk[z, y, x] = 1
+    cflag = ((usage > 0).astype(np.uint8) | (((apnet != 0) & (apnet != net)).astype(np.uint8) << 1) | (blk << 2))
+    srcs = [tuple(int(v) for v in inst.ap_xyz[i]) for i in range(len(inst.ap_net)) if inst.ap_net[i] == net][:2]
+    want = brute_force_dist(g, cflag, srcs)
+    got = env.distance_field(net, [ci(g, *s) for s in srcs]).astype(np.int64)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_paths_are_consistent_with_costs_and_metrics(seed):
+    """Every committed path is connected, its weight sum equals the reported connection cost,
+    early-terminated and full Dijkstra agree, and the deltas add up to the cumulative metrics."""
+    g = ispd18_geometry(20, 18, 4)
+    inst = make_instance(g, 8, 40 + seed, p_obstacle=0.25)
+    a, b = OracleEnv(g, inst), OracleEnv(g, inst)
+    tot = np.zeros(3, np.int64)
+    for net in np.random.default_rng(seed).permutation(inst.net_ids):
+        ma, mb = a.step(int(net)), b.step(int(net), full=True)
+        assert ma == mb
+        pa, pb = a.last_paths(), b.last_paths()
+        assert all(np.array_equal(x, y) for x, y in zip(pa, pb))
+        cells, off, cost = pa
+        wl = via = 0
+        for k in range(len(cost)):
+            seg = cells[off[k]:off[k + 1]]
+            for u, v in zip(seg[:-1], seg[1:]):
+                ux, uy, uz = u % g.X, (u // g.X) % g.Y, u // (g.X * g.Y)
+                vx, vy, vz = v % g.X, (v // g.X) % g.Y, v // (g.X * g.Y)
+                assert abs(ux - vx) + abs(uy - vy) + abs(uz - vz) == 1
+                via += uz != vz
+                wl += abs(int(g.x_coords[ux]) - int(g.x_coords[vx])) + abs(int(g.y_coords[uy]) - int(g.y_coords[vy]))
+        assert (ma["d_wirelength"], ma["d_via"]) == (wl, via)
+        tot += [ma["d_violation"], ma["d_wirelength"], ma["d_via"]]
+        assert tot.tolist() == [ma["violation"], ma["wirelength"], ma["via"]]
+        assert ma["violation"] == ma["blocked"] + ma["shorted"]
+    with pytest.raises(ValueError):
+        a.step(int(inst.net_ids[0]))                    # already routed -> illegal

@@ -2,7 +2,7 @@
 //
 // Replaces the external TritonRoute maze search the reference reaches through
 // ZMQ (baseline/baseline_utils.py:409-419).  Specification: DESIGN.md section 3;
-// CPU restatement: oracle/xr_oracle.c (dijkstra / backtrace / orc_step).
+// the CPU checker used by the tests restates the same specification independently.
 //
 // The search is a Bellman-Ford fixpoint computed with line sweeps (GAMER style):
 //   k_sweep_xz : for every row (y,z) a forward and a backward min-plus scan along
