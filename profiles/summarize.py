@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
+
+    python profiles/summarize.py launches gpurun_out/launches.csv "header text"  > profiles/xx_launches_summary.txt
+    python profiles/summarize.py full gpurun_out/prof_k.ncu-rep [...]             > profiles/xx_ncu_full_summary.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__grid_size', 'launch__block_size', 'launch__cluster_size', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'launch__waves_per_multiprocessor',
+        'smsp__inst_executed.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'lts__t_bytes.sum', 'launch__shared_mem_per_block_dynamic']
+
+
+def launches(path, header):
+    print("#", header)
+    print("# per-launch times are cold-cache and serialised under ncu: compare SHARES, not absolutes")
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    kn, mv, mn, mu = (hdr.index(k) for k in ('Kernel Name', 'Metric Value', 'Metric Name', 'Metric Unit'))
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in data:
+        if len(r) <= mv or r[mn] != 'gpu__time_duration.sum':
+            continue
+        v = float(r[mv].replace(',', ''))
+        v *= {'ns': 1, 'us': 1e3, 'ms': 1e6, 's': 1e9}.get(r[mu], 1)
+        name = r[kn].split('(')[0]
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:44s} n={v[0]:5d} total={v[1] / 1e6:9.3f} ms avg={v[1] / v[0] / 1e3:9.2f} us share={v[1] / tot:.3f}")
+
+
+def full(paths):
+    for p in paths:
+        out = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr = rows[0]
+        kn = hdr.index('Kernel Name') if 'Kernel Name' in hdr else None
+        print("==", p, "| kernel:", rows[2][kn].split('(')[0] if kn is not None and len(rows) > 2 else '?',
+              "| one column per captured launch (first row = unit)")
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print("  ", w, [r[i] for r in rows[1:]])
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    else:
+        full(sys.argv[2:])
