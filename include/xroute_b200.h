@@ -72,7 +72,11 @@ typedef struct XrConfig {
     const int32_t *layer_min_width;  /* [Z] DBU                                              */
     int32_t via_cost, grid_cost, drc_cost, fixed_shape_cost, block_cost; /* router constants */
     int32_t pumps_per_sync;    /* relaxation iterations launched between host polls; 0 = default */
-    int32_t reserved[7];
+    int32_t window_margin;     /* cells added around a net's AP bounding box for the on-chip window
+                                  search; 0 = default (10), <0 = always use the full-grid sweeps  */
+    int32_t min_cluster;       /* smallest CTA cluster per environment for the window kernel
+                                  (1, 2, 4 or 8); 0 = default (1)                               */
+    int32_t reserved[5];
 } XrConfig;
 
 /* cumulative metric slots of xr_step_results / XR_BUF_CUM */
@@ -96,7 +100,7 @@ enum { XR_S_STEPS = 0, XR_S_EPISODES = 1, XR_S_VIOLATION = 2, XR_S_WIRELENGTH = 
 
 /* kernel classes of xr_profile_get */
 enum { XR_K_OBS = 0, XR_K_METRICS = 1, XR_K_ROUTE_BEGIN = 2, XR_K_SWEEP_XZ = 3, XR_K_SWEEP_Y = 4,
-       XR_K_CONTROL = 5, XR_K_REINIT = 6, XR_K_MISC = 7, XR_K_COUNT = 8 };
+       XR_K_CONTROL = 5, XR_K_ROUTE_WIN = 6, XR_K_MISC = 7, XR_K_COUNT = 8 };
 
 int  xr_version(void);
 int  xr_create(const XrConfig *cfg, XrEnv **out);
@@ -158,6 +162,9 @@ int xr_stats_update(XrEnv *env, void *stream);
  * passes / cells relaxed by the maze kernels.                                   */
 int xr_counters(const XrEnv *env, int64_t *kernel_launches, int64_t *relax_passes,
                 int64_t *cells_relaxed, int64_t *host_syncs);
+/* Route-path usage since creation: nets routed by the window kernel, nets that started
+ * on the full-grid path, and window searches handed over to it (exit test failed).  */
+int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, int64_t *window_fallbacks);
 
 /* Per-kernel-class device timing with CUDA events on the launching stream.
  * enable: 0/1.  xr_profile_get synchronises and returns accumulated milliseconds

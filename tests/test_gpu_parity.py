@@ -60,6 +60,32 @@ def test_episode_small_grids(shape):
     _run_episode(geom, insts, seed=shape[1])
 
 
+@pytest.mark.parametrize("kw", [dict(window_margin=-1), dict(window_margin=1), dict(window_margin=3, min_cluster=2),
+                                dict(min_cluster=4), dict(min_cluster=8), dict(window_margin=30)],
+                         ids=["global-only", "margin1-fallbacks", "margin3-c2", "c4", "c8", "margin30"])
+def test_route_paths_agree_across_engines(kw):
+    """Window kernel (every cluster size), forced fall-backs to the full-grid sweeps and the
+    full-grid path alone must all reproduce the oracle bit-exactly."""
+    geom = ispd18_geometry(48, 44, 9)
+    insts = make_batch(geom, 5, 10, seed=900, p_obstacle=0.2)
+    _run_episode(geom, insts, seed=8, **kw)
+
+
+def test_window_fallback_counter_and_exactness():
+    from xroute_env_b200 import VecGame
+    geom = ispd18_geometry(64, 64, 9)
+    insts = make_batch(geom, 4, 12, seed=910, p_obstacle=0.3)
+    _run_episode(geom, insts, seed=9, window_margin=1)
+    vg = VecGame(geom, insts, device=0, window_margin=1)
+    vg.reset()
+    for net in (1, 2, 3, 4, 5, 6):
+        vg.step(np.array([net] * 4, np.int32))
+    rc = vg.route_counters()
+    assert rc["window_nets"] == 24 and rc["global_nets"] == 0
+    assert rc["window_fallbacks"] >= 1, "margin 1 with 30% blockage must trip the exit test somewhere"
+    vg.close()
+
+
 def test_episode_t1_7x7():
     geom = ispd18_geometry(112, 116, 9)
     insts = make_batch(geom, 4, 16, seed=5)

@@ -19,7 +19,7 @@ XR_STATS_COUNT = 16
 XR_K_COUNT = 8
 (XR_BUF_OBS, XR_BUF_DELTA, XR_BUF_CUM, XR_BUF_DONE, XR_BUF_NREMAIN, XR_BUF_LEGAL, XR_BUF_STATS,
  XR_BUF_REWARD) = range(8)
-K_NAMES = ["obs", "metrics", "route_begin", "sweep_xz", "sweep_y", "control", "reinit", "misc"]
+K_NAMES = ["obs", "metrics", "route_begin", "sweep_xz", "sweep_y", "control", "route_win", "misc"]
 STAT_NAMES = ["steps", "episodes", "violation", "wirelength", "via", "blocked", "shorted", "overflow",
               "reward_x2", "relax_passes", "cells_relaxed", "connections"]
 
@@ -35,7 +35,8 @@ class XrConfig(C.Structure):
         ("layer_pitch", C.POINTER(C.c_int32)), ("layer_min_width", C.POINTER(C.c_int32)),
         ("via_cost", C.c_int32), ("grid_cost", C.c_int32), ("drc_cost", C.c_int32),
         ("fixed_shape_cost", C.c_int32), ("block_cost", C.c_int32),
-        ("pumps_per_sync", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("pumps_per_sync", C.c_int32), ("window_margin", C.c_int32), ("min_cluster", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -55,7 +56,7 @@ SYMBOLS = [
     "xr_step", "xr_step_results", "xr_obs_layout", "xr_obs_channels", "xr_obs_copy",
     "xr_obs_dlpack", "xr_buffer_dlpack", "xr_buffer_ptr", "xr_legal_mask", "xr_get_paths",
     "xr_get_state", "xr_get_dist", "xr_stats_update", "xr_counters", "xr_profile_enable",
-    "xr_profile_get", "xr_build_obs_from_nodes",
+    "xr_profile_get", "xr_build_obs_from_nodes", "xr_route_counters",
 ]
 
 _lib = None
@@ -112,6 +113,8 @@ def load():
     L.xr_stats_update.argtypes = [vp, vp]
     L.xr_counters.restype = C.c_int
     L.xr_counters.argtypes = [vp, i64p, i64p, i64p, i64p]
+    L.xr_route_counters.restype = C.c_int
+    L.xr_route_counters.argtypes = [vp, i64p, i64p, i64p]
     L.xr_profile_enable.restype = C.c_int
     L.xr_profile_enable.argtypes = [vp, C.c_int32]
     L.xr_profile_get.restype = C.c_int

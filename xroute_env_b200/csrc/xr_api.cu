@@ -10,6 +10,7 @@
 #include "xr_common.cuh"
 #include "xr_kernels_env.cuh"
 #include "xr_kernels_maze.cuh"
+#include "xr_kernels_win.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -40,6 +41,12 @@ struct XrEnv {
     int32_t *p_ids = nullptr;           // pinned [N]
     int32_t *d_ids = nullptr;
     int pumps_per_sync = 4;
+    // window-resident route kernel
+    int win_margin = 10, min_cluster = 1, smem_cap = 0;
+    std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
+    int32_t *p_lists = nullptr;         // pinned [5][N]: mode + env lists of the 4 cluster buckets
+    int32_t *d_lists = nullptr;         // device [4][N]
+    long long n_win_nets = 0, n_global_nets = 0;
     // counters
     long long n_launch = 0, n_sync = 0;
     // profiling
@@ -118,6 +125,7 @@ static void xr_free(XrEnv *env) {
     if (env->p_act) cudaFreeHost(env->p_act);
     if (env->p_flags) cudaFreeHost(env->p_flags);
     if (env->p_ids) cudaFreeHost(env->p_ids);
+    if (env->p_lists) cudaFreeHost(env->p_lists);
     for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : env->ev_pool) cudaEventDestroy(e);
     delete env;
@@ -209,6 +217,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(env->d_lists, N * 4);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -225,7 +234,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
 #undef DA
     if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
-        cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess) {
+        cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
+        cudaMallocHost(&env->p_lists, sizeof(int32_t) * 5 * N) != cudaSuccess) {
         xr_free(env);
         return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
     }
@@ -234,6 +244,14 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_npins.assign(N * (g.max_nets + 1), 0);
     env->h_done.assign(N, 0); env->h_loaded.assign(N, 0); env->h_reset.assign(N, 0);
     env->h_nrem.assign(N, 0);
+    env->h_netwin.assign(N * (g.max_nets + 1) * 2, 0);
+    env->win_margin = cfg->window_margin == 0 ? 10 : cfg->window_margin;
+    env->min_cluster = cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2 : 1;
+    cudaDeviceGetAttribute(&env->smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    cudaFuncSetAttribute(k_route_win<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     // dynamic shared memory of the x+z sweep
     const int smem = g.Z * g.Xp * 5;
     cudaFuncSetAttribute(k_sweep_xz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -285,6 +303,11 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
     std::vector<int32_t> cellp(g.max_aps, 0), obsoff(g.max_aps, 0), nstart(g.max_nets + 2, 0);
     std::vector<uint16_t> pin(g.max_aps, 0), srcpin(g.max_nets + 1, 0);
     std::vector<uint8_t> adj(g.max_aps, 0);
+    std::vector<int32_t> netwin((size_t)(g.max_nets + 1) * 6, 0);
+    for (int net = 0; net <= g.max_nets; net++) {
+        env->h_netwin[((size_t)env_id * (g.max_nets + 1) + net) * 2] = 0;
+        env->h_netwin[((size_t)env_id * (g.max_nets + 1) + net) * 2 + 1] = 0;
+    }
     std::vector<int> sx(n_ap), sy(n_ap), sz(n_ap), snet(n_ap);
     for (int k = 0; k < n_ap; k++) {
         const int i = order[k];
@@ -330,6 +353,17 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
         }
         srcpin[net] = (uint16_t)bp;
         if (np - 1 > g.conn_cap) return fail(env, XR_E_CAPACITY, "net has more than 257 pins");
+        // window of the on-chip search: AP bounding box + margin, clipped to the grid
+        if (env->win_margin > 0) {
+            const int m = env->win_margin;
+            const int wx0 = std::max(0, xmin - m), wx1 = std::min(g.X - 1, xmax + m);
+            const int wy0 = std::max(0, ymin - m), wy1 = std::min(g.Y - 1, ymax + m);
+            int32_t *w = &netwin[(size_t)net * 6];
+            w[0] = wx0 | (wy0 << 16); w[1] = (wx1 - wx0 + 1) | ((wy1 - wy0 + 1) << 16);
+            w[2] = env->xc[xmin]; w[3] = env->xc[xmax]; w[4] = env->yc[ymin]; w[5] = env->yc[ymax];
+            env->h_netwin[((size_t)env_id * (g.max_nets + 1) + net) * 2] = wx1 - wx0 + 1;
+            env->h_netwin[((size_t)env_id * (g.max_nets + 1) + net) * 2 + 1] = wy1 - wy0 + 1;
+        }
     }
     const Dev &d = env->d;
     const size_t e = env_id;
@@ -341,6 +375,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
     CK(cudaMemcpy(d.ap_adj + e * g.max_aps, adj.data(), g.max_aps, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.net_start + e * (g.max_nets + 2), nstart.data(), sizeof(int32_t) * (g.max_nets + 2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.net_srcpin + e * (g.max_nets + 1), srcpin.data(), sizeof(uint16_t) * (g.max_nets + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.net_win + e * (g.max_nets + 1) * 6, netwin.data(), sizeof(int32_t) * (g.max_nets + 1) * 6, cudaMemcpyHostToDevice));
     env->h_loaded[env_id] = 1;
     env->h_reset[env_id] = 0;
     return XR_OK;
@@ -443,6 +478,25 @@ static void launch_sweep_y(XrEnv *env, cudaStream_t st) {
     else launch_y<64>(env, st);
 }
 
+template <int C>
+static cudaError_t launch_win_t(XrEnv *env, cudaStream_t st, int n_envs, const int *list) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_envs * C)); cfg.blockDim = dim3(WIN_T);
+    cfg.dynamicSmemBytes = (size_t)env->smem_cap; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_route_win<C>, env->g, env->d, list);
+}
+static int launch_route_win(XrEnv *env, cudaStream_t st, int C, int n_envs, const int *list) {
+    Launch L(env, XR_K_ROUTE_WIN, st);
+    cudaError_t e = C == 1 ? launch_win_t<1>(env, st, n_envs, list) : C == 2 ? launch_win_t<2>(env, st, n_envs, list)
+                  : C == 4 ? launch_win_t<4>(env, st, n_envs, list) : launch_win_t<8>(env, st, n_envs, list);
+    if (e != cudaSuccess) { env->err = std::string("k_route_win launch: ") + cudaGetErrorString(e); return XR_E_CUDA; }
+    return XR_OK;
+}
+
 extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     if (!env || !actions) return XR_E_INVALID;
     const Geo &g = env->g;
@@ -463,22 +517,61 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         }
         any_act = true;
     }
-    // p_act is reused across calls: the previous step's upload must have completed
+    // p_act / p_lists are reused across calls: the previous step's uploads must have completed
     CK(cudaStreamSynchronize(st)); env->n_sync++;
+    static const int CS[4] = {1, 2, 4, 8};
+    int nb[4] = {0, 0, 0, 0};
+    bool any_global = false;
+    int32_t *modes = env->p_lists;                        // [N], then 4 lists of N
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
-        int route = 0;
-        if (a >= 1 && env->h_npins[(size_t)i * (g.max_nets + 1) + a] >= 2) { route = a; any_route = true; }
+        int route = 0, mode = 0;
+        if (a >= 1 && env->h_npins[(size_t)i * (g.max_nets + 1) + a] >= 2) {
+            route = a; any_route = true;
+            const int WX = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2];
+            const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
+            int bucket = -1;
+            if (WX > 0) {
+                for (int b = 0; b < 4 && bucket < 0; b++) {
+                    if (CS[b] < env->min_cluster) continue;
+                    const int H = (WY + CS[b] - 1) / CS[b];
+                    const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H + 2, WX));
+                    if (bytes <= env->smem_cap && (CS[b] == 1 || H >= 1)) bucket = b;
+                }
+            }
+            if (bucket >= 0) { mode = 1; env->p_lists[(size_t)(1 + bucket) * g.N + nb[bucket]++] = i; env->n_win_nets++; }
+            else { any_global = true; env->n_global_nets++; }
+        }
         env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
+        modes[i] = mode;
     }
     CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * 2 * g.N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(env->d.mode, modes, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     if (any_route) {
+        if (nb[0] + nb[1] + nb[2] + nb[3] > 0)
+            CK(cudaMemcpyAsync(env->d_lists, env->p_lists + g.N, sizeof(int32_t) * 4 * g.N, cudaMemcpyHostToDevice, st));
         Launch L(env, XR_K_ROUTE_BEGIN, st);
         k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d);
     }
     { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
     CK(cudaGetLastError());
-    if (any_route) {
+    bool need_global = any_global;
+    if (nb[0] + nb[1] + nb[2] + nb[3] > 0) {
+        for (int b = 0; b < 4; b++) {
+            if (!nb[b]) continue;
+            int rc = launch_route_win(env, st, CS[b], nb[b], env->d_lists + (size_t)b * g.N);
+            if (rc != XR_OK) return rc;
+        }
+        // did any window search hand its environment over to the full-grid path?
+        CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st)); env->n_sync++;
+        if (env->p_flags[1] != 0) {
+            cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
+            return fail(env, XR_E_UNROUTABLE, "window maze search failed (inconsistent backtrace)");
+        }
+        if (env->p_flags[0] > 0) need_global = true;
+    }
+    if (need_global) {
         long long pumps = 0;
         const long long guard = 64ll * (g.X + g.Y + g.Z) + 4096;
         for (;;) {
@@ -718,11 +811,23 @@ extern "C" int xr_counters(const XrEnv *env, int64_t *kernel_launches, int64_t *
         cudaDeviceSynchronize();
         std::vector<long long> es((size_t)g.N * 8);
         cudaMemcpy(es.data(), env->d.envstat, sizeof(long long) * 8 * g.N, cudaMemcpyDeviceToHost);
-        long long pumps = 0;
-        for (int i = 0; i < g.N; i++) pumps += es[8 * (size_t)i + 2];
-        if (relax_passes) *relax_passes = pumps * 2;
-        if (cells_relaxed) *cells_relaxed = pumps * 2 * (long long)g.cells;
+        long long passes = 0, cells = 0;
+        for (int i = 0; i < g.N; i++) { passes += es[8 * (size_t)i + 2]; cells += es[8 * (size_t)i + 7]; }
+        if (relax_passes) *relax_passes = passes;
+        if (cells_relaxed) *cells_relaxed = cells;
     }
+    return XR_OK;
+}
+
+extern "C" int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, int64_t *window_fallbacks) {
+    if (!env) return XR_E_INVALID;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    int fb = 0;
+    CK(cudaMemcpy(&fb, env->d.flags + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    if (window_nets) *window_nets = env->n_win_nets;
+    if (global_nets) *global_nets = env->n_global_nets;
+    if (window_fallbacks) *window_fallbacks = fb;
     return XR_OK;
 }
 

@@ -54,6 +54,7 @@ struct Dev {
     uint8_t  *ap_adj;     // [N][max_aps] AP has a 6-neighbour AP of the same net
     int32_t  *net_start;  // [N][max_nets+2]
     uint16_t *net_srcpin; // [N][max_nets+1]
+    int32_t  *net_win;    // [N][max_nets+1][6] window x0|y0<<16, WX|WY<<16, AP bbox DBU x0,x1,y0,y1
     // dynamic environment state
     uint8_t  *obst_obs;   // [N][cells_o] obstacle channel source, observation layout
     uint8_t  *routed;     // [N][max_nets+1]
@@ -64,12 +65,13 @@ struct Dev {
     uint32_t *dist;       // [N][cells_p]
     uint8_t  *cflag;      // [N][cells_p]
     int32_t  *act;        // [N][2] raw action, net to route (0 = none)
+    int32_t  *mode;       // [N] 0 = global full-grid sweeps, 1 = window-resident kernel
     int32_t  *phase;      // [N] 0 idle, 1 routing
     int32_t  *changed;    // [N]
     int32_t  *reinit;     // [N]
     int32_t  *first;      // [N]
     uint8_t  *ap_conn;    // [N][max_aps]
-    int32_t  *flags;      // [0] number of envs routing, [1] error flag
+    int32_t  *flags;      // [0] envs in the global route loop, [1] error flag, [2] window fallbacks
     // results
     unsigned int *msum;   // [N][4] blocked, shorted, overflow
     int32_t  *delta;      // [N][3]
@@ -77,7 +79,7 @@ struct Dev {
     long long *wlvia;     // [N][2] cumulative wirelength / via (commit time)
     uint8_t  *done;       // [N]
     double   *reward;     // [N]
-    long long *envstat;   // [N][8] steps, episodes, pumps, connections, sum dvio, sum dwl, sum dvia
+    long long *envstat;   // [N][8] steps, episodes, pumps, connections, sum dvio, sum dwl, sum dvia, cells relaxed; [2] counts relaxation passes
     long long *stats;     // [16]
     uint8_t  *obs_do;     // [N]
     float    *obs;        // [N][obs_stride]

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_stats(Geo g, Dev d) {
         acc[2] += es[4]; acc[3] += es[5]; acc[4] += es[6];     // lifetime sums of the step deltas
         acc[5] += cum[3]; acc[6] += cum[4]; acc[7] += cum[5];  // congestion snapshot of the running episodes
         acc[8] += -(es[4] * 1000 + es[6] * 8 + es[5]);         // 2 * lifetime reward (exact integer)
-        acc[9] += es[2] * 2; acc[10] += es[2] * 2 * (long long)g.cells; acc[11] += es[3];
+        acc[9] += es[2]; acc[10] += es[7]; acc[11] += es[3];
     }
     __shared__ long long sm[12][8];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;

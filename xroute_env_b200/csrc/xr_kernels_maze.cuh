@@ -78,8 +78,11 @@ __global__ void k_seed(Geo g, Dev d) {
         }
     }
     if (threadIdx.x == 0) {
-        d.phase[env] = 1; d.changed[env] = 1; d.reinit[env] = 0; d.first[env] = 1;
-        atomicAdd(&d.flags[0], 1);
+        d.changed[env] = 1; d.reinit[env] = 0; d.first[env] = 1;
+        if (d.mode[env] == 0) {               // global path: arm the state machine now; the
+            d.phase[env] = 1;                 // window kernel arms it only if it has to fall back
+            atomicAdd(&d.flags[0], 1);
+        } else d.phase[env] = 0;
     }
 }
 
@@ -342,7 +345,9 @@ __device__ __forceinline__ void commit_cell(const Geo &g, const Dev &d, int env,
 __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
     const int env = blockIdx.x, lane = threadIdx.x;
     if (d.phase[env] != 1) return;
-    if (lane == 0) d.envstat[8 * (size_t)env + 2] += 1;          // one more pump (2 relaxation passes)
+    if (lane == 0) {                                     // one more pump = 2 full-grid relaxation passes
+        d.envstat[8 * (size_t)env + 2] += 2; d.envstat[8 * (size_t)env + 7] += 2ll * g.cells;
+    }
     if (d.changed[env] != 0) {                           // not converged yet
         __syncwarp();
         if (lane == 0) { d.changed[env] = 0; d.reinit[env] = 0; }

@@ -25,7 +25,8 @@ def _i32p(a: np.ndarray):
 class VecGame:
     def __init__(self, geom: Geometry, instances: list[Instance], *, device: int = 0,
                  max_nets: int | None = None, max_aps: int | None = None,
-                 obs_max_nets: int = -1, path_capacity: int = 0, pumps_per_sync: int = 0):
+                 obs_max_nets: int = -1, path_capacity: int = 0, pumps_per_sync: int = 0,
+                 window_margin: int = 0, min_cluster: int = 0):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.geom = geom
@@ -51,6 +52,7 @@ class VecGame:
         cfg.via_cost, cfg.grid_cost, cfg.drc_cost = geom.via_cost, geom.grid_cost, geom.drc_cost
         cfg.fixed_shape_cost, cfg.block_cost = geom.fixed_shape_cost, geom.block_cost
         cfg.pumps_per_sync = pumps_per_sync
+        cfg.window_margin, cfg.min_cluster = window_margin, min_cluster
         rc = self._L.xr_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()
@@ -221,6 +223,11 @@ class VecGame:
         _lib.check(self._L.xr_counters(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), self._h)
         return {"kernel_launches": a.value, "relax_passes": b.value, "cells_relaxed": c.value,
                 "host_syncs": d.value}
+
+    def route_counters(self) -> dict:
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self._L.xr_route_counters(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
+        return {"window_nets": a.value, "global_nets": b.value, "window_fallbacks": c.value}
 
     def profile(self, enable: bool):
         _lib.check(self._L.xr_profile_enable(self._h, int(enable)), self._h)
