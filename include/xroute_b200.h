@@ -165,6 +165,9 @@ int xr_counters(const XrEnv *env, int64_t *kernel_launches, int64_t *relax_passe
 /* Route-path usage since creation: nets routed by the window kernel, nets that started
  * on the full-grid path, and window searches handed over to it (exit test failed).  */
 int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, int64_t *window_fallbacks);
+/* Window-kernel diagnostics, uint64 [8]: iterations, connections, relax cycles, kernel
+ * cycles (rank-0 CTAs), nets, sum of window areas (cells per layer).                  */
+int xr_debug_counters(XrEnv *env, uint64_t *out);
 
 /* Per-kernel-class device timing with CUDA events on the launching stream.
  * enable: 0/1.  xr_profile_get synchronises and returns accumulated milliseconds

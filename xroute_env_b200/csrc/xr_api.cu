@@ -217,7 +217,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(env->d_lists, N * 4);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(env->d_lists, N * 4); DA(d.dbg, 8);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -828,6 +828,17 @@ extern "C" int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *glob
     if (window_nets) *window_nets = env->n_win_nets;
     if (global_nets) *global_nets = env->n_global_nets;
     if (window_fallbacks) *window_fallbacks = fb;
+    return XR_OK;
+}
+
+/* Diagnostics of the window kernel (not part of the stable ABI surface of the path):
+ * out[0] iterations, [1] connections, [2] relax cycles, [3] kernel cycles (rank-0 CTAs),
+ * [4] nets, [5] sum of window cells (x*y).                                            */
+extern "C" int xr_debug_counters(XrEnv *env, uint64_t *out) {
+    if (!env || !out) return XR_E_INVALID;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, env->d.dbg, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost));
     return XR_OK;
 }
 

@@ -81,6 +81,7 @@ struct Dev {
     double   *reward;     // [N]
     long long *envstat;   // [N][8] steps, episodes, pumps, connections, sum dvio, sum dwl, sum dvia, cells relaxed; [2] counts relaxation passes
     long long *stats;     // [16]
+    unsigned long long *dbg; // [8] window-kernel diagnostics: iterations, connections, relax cycles, kernel cycles, nets, window cells
     uint8_t  *obs_do;     // [N]
     float    *obs;        // [N][obs_stride]
     // last routed paths (parity / debug)

@@ -30,7 +30,8 @@ namespace cg = cooperative_groups;
 #define WIN_T 512
 #define WMASK 0x0FFFFFFFu
 #define WINF 0x0FFFFFFFu
-#define WIN_AUX_WORDS(Z, HH, WX) (3 * (Z) * 8 + (WX) + 2 + (HH) + 2 + 64)
+#define WIN_TGT_CAP 256
+#define WIN_AUX_WORDS(Z, HH, WX) (3 * (Z) * 8 + (WX) + 2 + (HH) + 2 + 64 + 2 * WIN_TGT_CAP)
 
 struct WinCtx {
     uint32_t *cell;      // [Z][HH][WXp]
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     c.lenx = aux; aux += WX + 2;
     c.leny = aux; aux += c.HH + 2;
     unsigned long long *s_best = reinterpret_cast<unsigned long long *>(aux + (aux - wsm) % 2);   // 8-byte aligned
-    int *s_flag = reinterpret_cast<int *>(s_best + 2);   // [0..1] changed (double buffered), [2] exit-check, [3] state
+    int *s_flag = reinterpret_cast<int *>(s_best + 2);   // [0..1] changed (double buffered), [2] exit-check, [3] state, [4] #targets
+    int *s_tgt = s_flag + 8;                             // [WIN_TGT_CAP][2] DBU coordinates of the unconnected APs
     // ---- tables
     for (int i = tid; i < 3 * c.Z * 8; i += WIN_T) {
         const int axis = i / (c.Z * 8), z = (i / 8) % c.Z, f = i & 7;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         }
         c.cell[i] = v;
     }
-    if (tid < 4) s_flag[tid] = 0;
+    if (tid < 8) s_flag[tid] = 0;
     __syncthreads();
     // ---- seeds: access points of the source pin inside this band
     const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
@@ -202,14 +204,18 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         if (ly >= 1 && ly <= c.h) c.cell[((size_t)z * c.HH + ly) * c.WXp + x] &= ~WMASK;
     }
     bool first = true;
-    long long relaxed = 0;
+    long long relaxed = 0, cyc_relax = 0;
+    int n_iter = 0, n_conn = 0;
+    const long long tk0 = clock64();
     const bool open_x0 = wx0 > 0, open_x1 = wx0 + WX < g.X, open_y0 = wy0 > 0, open_y1 = wy0 + WY < g.Y;
     const int band_cells = c.Z * c.h * WX;
     int parity = 0;
     if (C > 1) cluster.sync(); else __syncthreads();
     for (;;) {                                            // ---- one connection per trip
         // ---- relax to the fixpoint
+        const long long tr0 = clock64();
         for (;;) {
+            n_iter++;
             if (C > 1) {
                 // pull the neighbours' boundary rows into the halo rows
                 for (int i = tid; i < 2 * c.Z * WX; i += WIN_T) {
@@ -243,11 +249,18 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
             } else if (!anyc) break;
         }
         // ---- best target in this band + window-exit test
+        const long long tq0 = clock64();
+        cyc_relax += tq0 - tr0; n_conn++;
+        if (tid == 0) { s_best[0] = ~0ull; s_flag[4] = 0; }
+        __syncthreads();
         unsigned long long best = ~0ull;
         for (int i = s + tid; i < t; i += WIN_T) {
             if (d.ap_conn[aoff + i]) continue;
             const int cp = d.ap_cellp[aoff + i];
-            const int x = cp % g.Xp - wx0, wy = (cp / g.Xp) % g.Y - wy0, z = cp / (g.Xp * g.Y);
+            const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
+            const int k = atomicAdd(&s_flag[4], 1);          // every CTA keeps the full target list
+            if (k < WIN_TGT_CAP) { s_tgt[2 * k] = g.xc[gx]; s_tgt[2 * k + 1] = g.yc[gy]; }
+            const int x = gx - wx0, wy = gy - wy0;
             const int ly = wy - c.ry0 + 1;
             if (ly < 1 || ly > c.h) continue;
             const uint32_t dv = c.cell[((size_t)z * c.HH + ly) * c.WXp + x] & WMASK;
@@ -259,8 +272,6 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
             const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, best, off);
             best = o < best ? o : best;
         }
-        if (tid == 0) s_best[0] = ~0ull;
-        __syncthreads();
         if (lane == 0 && best != ~0ull) atomicMin(&s_best[0], best);
         if (C > 1) cluster.sync(); else __syncthreads();
         best = ~0ull;
@@ -268,6 +279,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
             const unsigned long long o = (C > 1) ? *cluster.map_shared_rank(&s_best[0], r) : s_best[0];
             best = o < best ? o : best;
         }
+        const int n_tgt = s_flag[4];
         const uint32_t B = (uint32_t)(best >> 32);
         // exit test over the open faces of the band
         bool esc = (best == ~0ull) || B >= WINF;
@@ -287,10 +299,23 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                 if (!open) continue;
                 const uint32_t dv = c.cell[((size_t)z * c.HH + ly) * c.WXp + x] & WMASK;
                 if (dv >= WINF) continue;
+                if (dv > B) continue;
                 const int px = g.xc[wx0 + x], py = g.yc[wy0 + c.ry0 + ly - 1];
-                const uint32_t hx = px < bx0 ? bx0 - px : (px > bx1 ? px - bx1 : 0);
-                const uint32_t hy = py < by0 ? by0 - py : (py > by1 ? py - by1 : 0);
-                if (dv + hx + hy <= B) esc = true;
+                // admissible remaining cost: L1 track distance (>= 1 cost unit per DBU) to the
+                // nearest unconnected access point; bounding box of all APs if the list overflowed
+                uint32_t hmin;
+                if (n_tgt <= WIN_TGT_CAP) {
+                    hmin = 0xFFFFFFFFu;
+                    for (int j = 0; j < n_tgt; j++) {
+                        const uint32_t hh = (uint32_t)(abs(px - s_tgt[2 * j]) + abs(py - s_tgt[2 * j + 1]));
+                        hmin = hh < hmin ? hh : hmin;
+                    }
+                } else {
+                    const uint32_t hx = px < bx0 ? bx0 - px : (px > bx1 ? px - bx1 : 0);
+                    const uint32_t hy = py < by0 ? by0 - py : (py > by1 ? py - by1 : 0);
+                    hmin = hx + hy;
+                }
+                if (dv + hmin <= B) esc = true;
             }
         }
         const int esc_any = __syncthreads_or(esc);
@@ -454,6 +479,11 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         if (C > 1) cluster.sync(); else __syncthreads();
     }
     // relaxation accounting (cells touched by the in-window sweeps)
+    if (tid == 0 && rank == 0 && d.dbg) {
+        atomicAdd(&d.dbg[0], (unsigned long long)n_iter); atomicAdd(&d.dbg[1], (unsigned long long)n_conn);
+        atomicAdd(&d.dbg[2], (unsigned long long)cyc_relax); atomicAdd(&d.dbg[3], (unsigned long long)(clock64() - tk0));
+        atomicAdd(&d.dbg[4], 1ull); atomicAdd(&d.dbg[5], (unsigned long long)(WX * WY));
+    }
     if (tid == 0) {                                        // every thread counted the same band
         atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 7]), (unsigned long long)relaxed);
         if (rank == 0 && band_cells > 0)

@@ -229,6 +229,12 @@ class VecGame:
         _lib.check(self._L.xr_route_counters(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
         return {"window_nets": a.value, "global_nets": b.value, "window_fallbacks": c.value}
 
+    def debug_counters(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        _lib.check(self._L.xr_debug_counters(self._h, out), self._h)
+        names = ["win_iterations", "win_connections", "win_relax_cycles", "win_kernel_cycles", "win_nets", "win_area"]
+        return {k: int(out[i]) for i, k in enumerate(names)}
+
     def profile(self, enable: bool):
         _lib.check(self._L.xr_profile_enable(self._h, int(enable)), self._h)
 
