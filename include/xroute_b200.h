@@ -75,7 +75,7 @@ typedef struct XrConfig {
     int32_t window_margin;     /* cells added around a net's AP bounding box for the on-chip window
                                   search; 0 = default (10), <0 = always use the full-grid sweeps  */
     int32_t min_cluster;       /* smallest CTA cluster per environment for the window kernel
-                                  (1, 2, 4 or 8); 0 = default (1)                               */
+                                  (1, 2, 4 or 8); 0 = auto (from the number of routing environments) */
     int32_t reserved[5];
 } XrConfig;
 
@@ -165,7 +165,7 @@ int xr_counters(const XrEnv *env, int64_t *kernel_launches, int64_t *relax_passe
 /* Route-path usage since creation: nets routed by the window kernel, nets that started
  * on the full-grid path, and window searches handed over to it (exit test failed).  */
 int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, int64_t *window_fallbacks);
-/* Window-kernel diagnostics, uint64 [8]: iterations, connections, relax cycles, kernel
+/* Window-kernel diagnostics, uint64 [16] ([8..14] per-phase cycles when built with -DWIN_PHASE_TIMING): iterations, connections, relax cycles, kernel
  * cycles (rank-0 CTAs), nets, sum of window areas (cells per layer).                  */
 int xr_debug_counters(XrEnv *env, uint64_t *out);
 

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libxroute_b200.so")
+SO_PATH = os.environ.get("XROUTE_B200_LIB", os.path.join(_HERE, "libxroute_b200.so"))   # override: A/B builds
 
 XR_OK = 0
 XR_E_INVALID, XR_E_CUDA, XR_E_ILLEGAL, XR_E_CAPACITY, XR_E_UNROUTABLE, XR_E_STATE = -1, -2, -3, -4, -5, -6

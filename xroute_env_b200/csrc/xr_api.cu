@@ -42,7 +42,7 @@ struct XrEnv {
     int32_t *d_ids = nullptr;
     int pumps_per_sync = 4;
     // window-resident route kernel
-    int win_margin = 10, min_cluster = 1, smem_cap = 0;
+    int win_margin = 10, min_cluster = 0, smem_cap = 0, n_sm = 148;
     std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
     int32_t *p_lists = nullptr;         // pinned [5][N]: mode + env lists of the 4 cluster buckets
     int32_t *d_lists = nullptr;         // device [4][N]
@@ -150,6 +150,9 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         return fail(nullptr, XR_E_INVALID, "geometry arrays missing");
     if ((long long)cfg->X * cfg->Y * cfg->Z >= (1ll << 30))
         return fail(nullptr, XR_E_INVALID, "grid too large");
+    if (cfg->via_cost < 1 || cfg->grid_cost < 0 || cfg->drc_cost < 0 || cfg->fixed_shape_cost < 0 || cfg->block_cost < 0 ||
+        1 + cfg->grid_cost + cfg->drc_cost + cfg->fixed_shape_cost > 255)
+        return fail(nullptr, XR_E_INVALID, "cost constants out of range (1 + grid + drc + fixed must be <= 255)");
     cudaError_t ce = cudaSetDevice(cfg->device);
     if (ce != cudaSuccess) return fail(nullptr, XR_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
     XrEnv *env = new XrEnv();
@@ -217,7 +220,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(env->d_lists, N * 4); DA(d.dbg, 8);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(env->d_lists, N * 4); DA(d.dbg, 16);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -246,7 +249,10 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_nrem.assign(N, 0);
     env->h_netwin.assign(N * (g.max_nets + 1) * 2, 0);
     env->win_margin = cfg->window_margin == 0 ? 10 : cfg->window_margin;
-    env->min_cluster = cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2 : 1;
+    // 0 = auto: per step, as many CTAs per environment as keeps about two clusters per SM's worth
+    env->min_cluster = cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2
+                     : cfg->min_cluster == 1 ? 1 : 0;
+    cudaDeviceGetAttribute(&env->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     cudaDeviceGetAttribute(&env->smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     cudaFuncSetAttribute(k_route_win<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
@@ -521,6 +527,14 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     CK(cudaStreamSynchronize(st)); env->n_sync++;
     static const int CS[4] = {1, 2, 4, 8};
     int nb[4] = {0, 0, 0, 0};
+    int min_cluster = env->min_cluster;
+    if (min_cluster == 0) {
+        int n_route = 0;
+        for (int i = 0; i < g.N; i++)
+            n_route += actions[i] >= 1 && env->h_npins[(size_t)i * (g.max_nets + 1) + actions[i]] >= 2;
+        min_cluster = 1;
+        while (min_cluster < 8 && n_route * min_cluster * 2 <= 2 * env->n_sm) min_cluster <<= 1;
+    }
     bool any_global = false;
     int32_t *modes = env->p_lists;                        // [N], then 4 lists of N
     for (int i = 0; i < g.N; i++) {
@@ -533,10 +547,10 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             int bucket = -1;
             if (WX > 0) {
                 for (int b = 0; b < 4 && bucket < 0; b++) {
-                    if (CS[b] < env->min_cluster) continue;
+                    if (CS[b] < min_cluster) continue;
                     const int H = (WY + CS[b] - 1) / CS[b];
-                    const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H + 2, WX));
-                    if (bytes <= env->smem_cap && (CS[b] == 1 || H >= 1)) bucket = b;
+                    const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX));
+                    if (bytes <= env->smem_cap) bucket = b;
                 }
             }
             if (bucket >= 0) { mode = 1; env->p_lists[(size_t)(1 + bucket) * g.N + nb[bucket]++] = i; env->n_win_nets++; }
@@ -838,7 +852,7 @@ extern "C" int xr_debug_counters(XrEnv *env, uint64_t *out) {
     if (!env || !out) return XR_E_INVALID;
     cudaSetDevice(env->device);
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out, env->d.dbg, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, env->d.dbg, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
     return XR_OK;
 }
 

@@ -30,102 +30,174 @@ namespace cg = cooperative_groups;
 #define WIN_T 512
 #define WMASK 0x0FFFFFFFu
 #define WINF 0x0FFFFFFFu
+#define WBLK 0x40000000u            // packed cell: [31] tree, [30] blockage, [29] fs, [28] rs, [27:0] dist
 #define WIN_TGT_CAP 256
-#define WIN_AUX_WORDS(Z, HH, WX) (3 * (Z) * 8 + (WX) + 2 + (HH) + 2 + 64 + 2 * WIN_TGT_CAP)
+// words of shared memory besides the cells: tables, target list, dirty flags, work list
+#define WIN_AUX_WORDS(Z, H, WX)                                                                   \
+    (3 * (Z) + 3 * (Z) + 24 * (Z) + (WX) + 2 + (H) + 4 + 64 + 2 * WIN_TGT_CAP +                                \
+     ((Z) * (H) + (Z) * (WX) + (H) * (WX)) / 4 + 3 + ((Z) * ((H) > (WX) ? (H) : (WX))) / 2 + 2)
 
 struct WinCtx {
     uint32_t *cell;      // [Z][HH][WXp]
-    uint32_t *lut;       // [3][Z][8]  mult | pen << 8
+    uint32_t *wlut;      // [3][Z][8] full edge weight per flag class when the axis has a uniform pitch
+    uint32_t *lutm;      // [3][Z]  four 8-bit multipliers (index = rs | fs<<1) per axis and layer
+    uint32_t *pens;      // [Z] blockage penalty, then [Z] via length below layer z, then [Z] above
     uint32_t *lenx;      // [WX+1]  lenx[lx] = xc[wx0+lx] - xc[wx0+lx-1]
     uint32_t *leny;      // [HH+1]  leny[ly] = yc[gy] - yc[gy-1], gy = wy0 + ry0 + ly - 1
-    int Z, WX, WXp, HH, h; // h = real rows of this CTA (local rows 1..h)
+    uint8_t *rowd, *cold, *posd;   // dirty flags: row (z,ly) / column (z,x) / via stack (ly,x)
+    uint16_t *list;      // compacted dirty lines
+    int *cnt;
+    int Z, WX, WXp, HH, H, h;      // h = real rows of this CTA (local rows 1..h), H = band height
     int wx0, wy0, ry0;
+    int uni_x, uni_y;    // uniform pitch inside the window: weights come straight from wlut
 };
 
-__device__ __forceinline__ uint32_t win_w(const uint32_t *lutrow, uint32_t len, uint32_t f) {
-    const uint32_t e = lutrow[f & 7u];
-    return len * (e & 0xFFu) + (e >> 8);
+__device__ __forceinline__ uint32_t win_w(uint32_t lutreg, uint32_t pen, uint32_t len, uint32_t v) {
+    const uint32_t m = (lutreg >> ((v >> 25) & 0x18u)) & 0xFFu;
+    return len * m + ((v & WBLK) ? pen : 0u);
 }
 
-// one thread per (x, z) column of the band: forward from the upper halo, back from the lower
-__device__ bool win_sweep_y(const WinCtx &c) {
+// Collect the set flags of flags[0..n) into c.list (clearing them); returns the count.
+__device__ int win_compact(const WinCtx &c, uint8_t *flags, int n) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) *c.cnt = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += WIN_T) {
+        const int i = i0 + threadIdx.x;
+        const bool f = i < n && flags[i];
+        if (f) flags[i] = 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, f);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(c.cnt, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (f) c.list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    return *c.cnt;
+}
+
+// Thread-per-line walk of n cells (element i at p[i*stride]) in direction DIR with carry-in
+// t; cells are fetched eight at a time so the shared-memory latency overlaps.  Used when
+// many lines are dirty (throughput bound: fewest instructions per cell).
+#define WIN_BATCH 8
+template <int DIR, bool UNI>
+__device__ __forceinline__ bool win_walk(uint32_t *__restrict__ p, int n, int stride, uint32_t t, uint32_t lutreg,
+                                         uint32_t pen, const uint32_t *__restrict__ len,
+                                         const uint32_t *__restrict__ wl,
+                                         uint8_t *__restrict__ fa, int sa, uint8_t *__restrict__ fb, int sb) {
     bool ch = false;
-    const int ncol = c.WX * c.Z;
-    for (int col = threadIdx.x; col < ncol; col += WIN_T) {
+    for (int i0 = 0; i0 < n; i0 += WIN_BATCH) {
+        uint32_t v[WIN_BATCH], w[WIN_BATCH];
+#pragma unroll
+        for (int k = 0; k < WIN_BATCH; k++) {
+            const int j = i0 + k;
+            const int i = DIR > 0 ? j : n - 1 - j;
+            v[k] = j < n ? p[i * stride] : 0xFFFFFFFFu;
+            if (!UNI) w[k] = j < n ? len[i + (DIR < 0 ? 1 : 0)] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < WIN_BATCH; k++) w[k] = UNI ? wl[(v[k] >> 28) & 7u] : win_w(lutreg, pen, w[k], v[k]);
+#pragma unroll
+        for (int k = 0; k < WIN_BATCH; k++) {
+            const int j = i0 + k;
+            if (j < n) {
+                const int i = DIR > 0 ? j : n - 1 - j;
+                const uint32_t dcur = v[k] & WMASK;
+                const uint32_t nd = xr_min(t + w[k], dcur);
+                if (nd < dcur) { p[i * stride] = (v[k] & ~WMASK) | nd; fa[i * sa] = 1; fb[i * sb] = 1; ch = true; }
+                t = nd;
+            }
+        }
+    }
+    return ch;
+}
+
+// one thread per dirty (z, x) column of the band: forward from the upper halo, back from the lower
+__device__ bool win_sweep_y(const WinCtx &c, int n, long long &work) {
+    bool ch = false;
+    for (int k = threadIdx.x; k < n; k += WIN_T) {
+        const int col = c.list[k];
         const int z = col / c.WX, x = col - z * c.WX;
         uint32_t *p = c.cell + (size_t)z * c.HH * c.WXp + x;
-        const uint32_t *lr = c.lut + (1 * c.Z + z) * 8;
-        uint32_t t = p[0] & WMASK;
-        for (int ly = 1; ly <= c.h; ly++) {
-            const uint32_t v = p[ly * c.WXp];
-            const uint32_t dcur = v & WMASK;
-            const uint32_t nd = xr_min(t + win_w(lr, c.leny[ly], v >> 28), dcur);
-            if (nd < dcur) { p[ly * c.WXp] = (v & ~WMASK) | nd; ch = true; }
-            t = nd;
+        const uint32_t lutreg = c.lutm[1 * c.Z + z], pen = c.pens[z];
+        const uint32_t *wl = c.wlut + (1 * c.Z + z) * 8;
+        if (c.uni_y) {
+            ch |= win_walk<1, true>(p + c.WXp, c.h, c.WXp, p[0] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                    c.rowd + z * c.H, 1, c.posd + x, c.WX);
+            ch |= win_walk<-1, true>(p + c.WXp, c.h, c.WXp, p[(c.h + 1) * c.WXp] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                     c.rowd + z * c.H, 1, c.posd + x, c.WX);
+        } else {
+            ch |= win_walk<1, false>(p + c.WXp, c.h, c.WXp, p[0] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                     c.rowd + z * c.H, 1, c.posd + x, c.WX);
+            ch |= win_walk<-1, false>(p + c.WXp, c.h, c.WXp, p[(c.h + 1) * c.WXp] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                      c.rowd + z * c.H, 1, c.posd + x, c.WX);
         }
-        t = p[(c.h + 1) * c.WXp] & WMASK;
-        for (int ly = c.h; ly >= 1; ly--) {
-            const uint32_t v = p[ly * c.WXp];
-            const uint32_t dcur = v & WMASK;
-            const uint32_t nd = xr_min(t + win_w(lr, c.leny[ly + 1], v >> 28), dcur);
-            if (nd < dcur) { p[ly * c.WXp] = (v & ~WMASK) | nd; ch = true; }
-            t = nd;
-        }
+        work += c.h;
     }
     return ch;
 }
 
-// one thread per (ly, z) row of the band
-__device__ bool win_sweep_x(const WinCtx &c) {
+// one thread per dirty (z, ly) row of the band
+__device__ bool win_sweep_x(const WinCtx &c, int n, long long &work) {
     bool ch = false;
-    const int nrow = c.h * c.Z;
-    for (int row = threadIdx.x; row < nrow; row += WIN_T) {
-        const int z = row / c.h, ly = row - z * c.h + 1;
+    for (int k = threadIdx.x; k < n; k += WIN_T) {
+        const int row = c.list[k];
+        const int z = row / c.H, ly = row - z * c.H + 1;
         uint32_t *p = c.cell + ((size_t)z * c.HH + ly) * c.WXp;
-        const uint32_t *lr = c.lut + (0 * c.Z + z) * 8;
-        uint32_t t = WINF;
-        for (int x = 0; x < c.WX; x++) {
-            const uint32_t v = p[x];
-            const uint32_t dcur = v & WMASK;
-            const uint32_t nd = xr_min(t + win_w(lr, c.lenx[x], v >> 28), dcur);
-            if (nd < dcur) { p[x] = (v & ~WMASK) | nd; ch = true; }
-            t = nd;
+        const uint32_t lutreg = c.lutm[0 * c.Z + z], pen = c.pens[z];
+        const uint32_t *wl = c.wlut + (0 * c.Z + z) * 8;
+        if (c.uni_x) {
+            ch |= win_walk<1, true>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
+            ch |= win_walk<-1, true>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
+        } else {
+            ch |= win_walk<1, false>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
+            ch |= win_walk<-1, false>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
         }
-        t = WINF;
-        for (int x = c.WX - 1; x >= 0; x--) {
-            const uint32_t v = p[x];
-            const uint32_t dcur = v & WMASK;
-            const uint32_t nd = xr_min(t + win_w(lr, c.lenx[x + 1], v >> 28), dcur);
-            if (nd < dcur) { p[x] = (v & ~WMASK) | nd; ch = true; }
-            t = nd;
-        }
+        work += c.WX;
     }
     return ch;
 }
 
-// one thread per (x, ly) position: up then down through the layers
-__device__ bool win_sweep_z(const WinCtx &c, const Geo &g) {
+// one thread per (ly, x) position whose via stack is dirty: up then down through the layers
+// (the Z cells are fetched first so their shared-memory latency overlaps)
+__device__ bool win_sweep_z(const WinCtx &c, long long &work) {
     bool ch = false;
     const int npos = c.WX * c.h;
     const size_t zs = (size_t)c.HH * c.WXp;
+    const uint32_t lutreg = c.lutm[2 * c.Z];
     for (int pos = threadIdx.x; pos < npos; pos += WIN_T) {
+        if (!c.posd[pos]) continue;
+        c.posd[pos] = 0;
         const int lyi = pos / c.WX, x = pos - lyi * c.WX;
         uint32_t *p = c.cell + (size_t)(lyi + 1) * c.WXp + x;
-        uint32_t t = p[0] & WMASK;
-        for (int z = 1; z < c.Z; z++) {
-            const uint32_t v = p[z * zs];
-            const uint32_t dcur = v & WMASK;
-            const uint32_t nd = xr_min(t + win_w(c.lut + (2 * c.Z + z) * 8, g.vlen[z - 1], v >> 28), dcur);
-            if (nd < dcur) { p[z * zs] = (v & ~WMASK) | nd; ch = true; }
-            t = nd;
+        uint32_t v[XR_ZMAX];
+#pragma unroll
+        for (int z = 0; z < XR_ZMAX; z++) v[z] = z < c.Z ? p[z * zs] : 0u;
+        unsigned chg = 0;
+        uint32_t t = v[0] & WMASK;
+#pragma unroll
+        for (int z = 1; z < XR_ZMAX; z++) if (z < c.Z) {
+            const uint32_t dcur = v[z] & WMASK;
+            t = xr_min(t + win_w(lutreg, c.pens[z], c.pens[c.Z + z], v[z]), dcur);
+            if (t < dcur) { v[z] = (v[z] & ~WMASK) | t; chg |= 1u << z; }
         }
-        for (int z = c.Z - 2; z >= 0; z--) {
-            const uint32_t v = p[z * zs];
-            const uint32_t dcur = v & WMASK;
-            const uint32_t nd = xr_min(t + win_w(c.lut + (2 * c.Z + z) * 8, g.vlen[z], v >> 28), dcur);
-            if (nd < dcur) { p[z * zs] = (v & ~WMASK) | nd; ch = true; }
-            t = nd;
+#pragma unroll
+        for (int z = XR_ZMAX - 2; z >= 0; z--) if (z < c.Z - 1) {
+            const uint32_t dcur = v[z] & WMASK;
+            t = xr_min(t + win_w(lutreg, c.pens[z], c.pens[2 * c.Z + z], v[z]), dcur);
+            if (t < dcur) { v[z] = (v[z] & ~WMASK) | t; chg |= 1u << z; }
         }
+        if (chg) {
+#pragma unroll
+            for (int z = 0; z < XR_ZMAX; z++) if (z < c.Z && ((chg >> z) & 1u)) {
+                p[z * zs] = v[z];
+                c.rowd[z * c.H + lyi] = 1; c.cold[z * c.WX + x] = 1;
+            }
+            ch = true;
+        }
+        work += c.Z;
     }
     return ch;
 }
@@ -140,6 +212,15 @@ __device__ __forceinline__ uint32_t *win_cell_ptr(cg::cluster_group &cluster, co
     return cluster.map_shared_rank(p, r);
 }
 
+// Mark the three lines through window cell (lx, wy, z) dirty in the CTA that owns it.
+template <int C>
+__device__ __forceinline__ void win_mark(cg::cluster_group &cluster, const WinCtx &c, int lx, int wy, int z) {
+    const int r = wy / c.H, lyi = wy - r * c.H;
+    uint8_t *rd = c.rowd + z * c.H + lyi, *cd = c.cold + z * c.WX + lx, *pd = c.posd + lyi * c.WX + lx;
+    if (C > 1) { rd = cluster.map_shared_rank(rd, r); cd = cluster.map_shared_rank(cd, r); pd = cluster.map_shared_rank(pd, r); }
+    *rd = 1; *cd = 1; *pd = 1;
+}
+
 template <int C>
 __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int *env_list) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -152,23 +233,42 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     const int bx0 = wd[2], bx1 = wd[3], by0 = wd[4], by1 = wd[5];      // DBU bbox of the net's APs
     const int H = (WY + C - 1) / C;
     WinCtx c;
-    c.Z = g.Z; c.WX = WX; c.WXp = WX | 1; c.HH = H + 2;
+    c.Z = g.Z; c.WX = WX; c.WXp = WX | 1; c.HH = H + 2; c.H = H;
     c.wx0 = wx0; c.wy0 = wy0; c.ry0 = rank * H;
     c.h = WY - c.ry0; if (c.h > H) c.h = H; if (c.h < 0) c.h = 0;
     extern __shared__ __align__(16) uint32_t wsm[];
     c.cell = wsm;
     uint32_t *aux = wsm + (size_t)c.Z * c.HH * c.WXp;
-    c.lut = aux; aux += 3 * c.Z * 8;
+    c.lutm = aux; aux += 3 * c.Z;
+    c.pens = aux; aux += 3 * c.Z;
+    c.wlut = aux; aux += 24 * c.Z;
+    c.uni_x = g.uniform_x; c.uni_y = g.uniform_y;
     c.lenx = aux; aux += WX + 2;
     c.leny = aux; aux += c.HH + 2;
-    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(aux + (aux - wsm) % 2);   // 8-byte aligned
-    int *s_flag = reinterpret_cast<int *>(s_best + 2);   // [0..1] changed (double buffered), [2] exit-check, [3] state, [4] #targets
-    int *s_tgt = s_flag + 8;                             // [WIN_TGT_CAP][2] DBU coordinates of the unconnected APs
+    aux += (aux - wsm) & 1;                                 // 8-byte alignment
+    unsigned long long *s_best = reinterpret_cast<unsigned long long *>(aux); aux += 4;
+    int *s_flag = reinterpret_cast<int *>(aux); aux += 8;   // [0..1] changed (double buffered), [2] exit, [3] more, [4] #targets, [5] list count
+    int *s_tgt = reinterpret_cast<int *>(aux); aux += 2 * WIN_TGT_CAP;   // DBU coordinates of the unconnected APs
+    c.cnt = &s_flag[5];
+    c.rowd = reinterpret_cast<uint8_t *>(aux);
+    c.cold = c.rowd + c.Z * H;
+    c.posd = c.cold + c.Z * WX;
+    c.list = reinterpret_cast<uint16_t *>(c.rowd + (((size_t)c.Z * H + c.Z * WX + (size_t)H * WX + 3) & ~(size_t)3));
+    const int n_flag_bytes = c.Z * H + c.Z * WX + H * WX;
     // ---- tables
-    for (int i = tid; i < 3 * c.Z * 8; i += WIN_T) {
-        const int axis = i / (c.Z * 8), z = (i / 8) % c.Z, f = i & 7;
+    for (int i = tid; i < 3 * c.Z; i += WIN_T) {
+        const int axis = i / c.Z, z = i - axis * c.Z;
+        uint32_t r = 0;
+        for (int f = 0; f < 4; f++)
+            r |= (axis == 0 ? g.multX[z][f] : axis == 1 ? g.multY[z][f] : g.multV[f]) << (8 * f);
+        c.lutm[i] = r;
+        c.pens[i] = axis == 0 ? g.pen[z] : axis == 1 ? (z >= 1 ? g.vlen[z - 1] : 0u) : g.vlen[z];
+    }
+    for (int i = tid; i < 24 * c.Z; i += WIN_T) {        // uniform-pitch weights per (axis, layer, flag class)
+        const int axis = i / (8 * c.Z), z = (i / 8) % c.Z, f = i & 7;
+        const uint32_t len = axis == 0 ? (uint32_t)g.dx : axis == 1 ? (uint32_t)g.dy : 0u;
         const uint32_t mult = axis == 0 ? g.multX[z][f & 3] : axis == 1 ? g.multY[z][f & 3] : g.multV[f & 3];
-        c.lut[i] = mult | (((f & 4) ? g.pen[z] : 0u) << 8);
+        c.wlut[i] = len * mult + ((f & 4) ? g.pen[z] : 0u);
     }
     for (int i = tid; i <= WX; i += WIN_T) {
         const int gx = wx0 + i;
@@ -178,6 +278,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         const int gy = wy0 + c.ry0 + i - 1;
         c.leny[i] = (gy >= 1 && gy < g.Y) ? (uint32_t)(g.yc[gy] - g.yc[gy - 1]) : 0u;
     }
+    for (int i = tid; i < n_flag_bytes; i += WIN_T) c.rowd[i] = 0;
     // ---- load the band: flags from the frozen cflag field, dist = INF; halo rows INF
     const size_t eoff = (size_t)env * g.cells_p;
     for (int i = tid; i < c.Z * c.HH * c.WXp; i += WIN_T) {
@@ -198,19 +299,26 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     const unsigned srcpin = d.net_srcpin[(size_t)env * (g.max_nets + 1) + net];
     for (int i = s + tid; i < t; i += WIN_T) {
         if (d.ap_pin[aoff + i] != srcpin) continue;
+        atomicAdd(&s_flag[6], 1);                        // every CTA counts all source APs
         const int cp = d.ap_cellp[aoff + i];
         const int x = cp % g.Xp - wx0, wy = (cp / g.Xp) % g.Y - wy0, z = cp / (g.Xp * g.Y);
         const int ly = wy - c.ry0 + 1;
-        if (ly >= 1 && ly <= c.h) c.cell[((size_t)z * c.HH + ly) * c.WXp + x] &= ~WMASK;
+        if (ly >= 1 && ly <= c.h) {
+            c.cell[((size_t)z * c.HH + ly) * c.WXp + x] &= ~WMASK;
+            c.rowd[z * H + ly - 1] = 1; c.cold[z * WX + x] = 1; c.posd[(ly - 1) * WX + x] = 1;
+        }
     }
     bool first = true;
-    long long relaxed = 0, cyc_relax = 0;
+    long long work = 0, cyc_relax = 0;
     int n_iter = 0, n_conn = 0;
+#ifdef WIN_PHASE_TIMING
+    long long ph[7] = {0, 0, 0, 0, 0, 0, 0};
+#endif
     const long long tk0 = clock64();
     const bool open_x0 = wx0 > 0, open_x1 = wx0 + WX < g.X, open_y0 = wy0 > 0, open_y1 = wy0 + WY < g.Y;
-    const int band_cells = c.Z * c.h * WX;
     int parity = 0;
     if (C > 1) cluster.sync(); else __syncthreads();
+    const int n_src_ap = s_flag[6];
     for (;;) {                                            // ---- one connection per trip
         // ---- relax to the fixpoint
         const long long tr0 = clock64();
@@ -228,17 +336,40 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                     const int dst_ly = side == 0 ? 0 : c.h + 1;
                     if (side == 1 && c.h < H) continue;   // no rows below a short (last) band
                     const uint32_t *rp = cluster.map_shared_rank(c.cell + ((size_t)z * c.HH + src_ly) * c.WXp + x, nr);
-                    c.cell[((size_t)z * c.HH + dst_ly) * c.WXp + x] = *rp;
+                    uint32_t *hp = c.cell + ((size_t)z * c.HH + dst_ly) * c.WXp + x;
+                    const uint32_t nv = *rp & WMASK;
+                    if (nv != (*hp & WMASK)) { *hp = nv; c.cold[z * WX + x] = 1; }
                 }
                 cluster.sync();
             }
-            bool ch = win_sweep_y(c);
+#ifdef WIN_PHASE_TIMING
+            const long long p0 = clock64();
+#endif
+            const int ny = win_compact(c, c.cold, c.Z * WX);
+#ifdef WIN_PHASE_TIMING
+            const long long p1 = clock64();
+#endif
+            bool ch = win_sweep_y(c, ny, work);
+#ifdef WIN_PHASE_TIMING
             __syncthreads();
-            ch |= win_sweep_x(c);
+            const long long p2 = clock64();
+#endif
+            const int nx = win_compact(c, c.rowd, c.Z * H);   // (its leading barrier closes the y sweep)
+#ifdef WIN_PHASE_TIMING
+            const long long p3 = clock64();
+#endif
+            ch |= win_sweep_x(c, nx, work);
             __syncthreads();
-            ch |= win_sweep_z(c, g);
-            relaxed += 3ll * band_cells;
+#ifdef WIN_PHASE_TIMING
+            const long long p4 = clock64();
+#endif
+            ch |= win_sweep_z(c, work);
             const int anyc = __syncthreads_or(ch);
+#ifdef WIN_PHASE_TIMING
+            const long long p5 = clock64();
+            ph[0] += p1 - p0; ph[1] += p2 - p1; ph[2] += p3 - p2; ph[3] += p4 - p3; ph[4] += p5 - p4;
+            ph[5] += ny; ph[6] += nx;
+#endif
             if (C > 1) {
                 if (tid == 0) s_flag[parity] = anyc;
                 cluster.sync();
@@ -376,6 +507,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                         if (lane < run) {
                             commit_cell(g, d, env, net, ax, ay, az);
                             *pa = (*pa & ~WMASK) | (CF_TREE << 28);
+                            win_mark<C>(cluster, c, ax - wx0, ay - wy0, az);
                             if (pn + lane < g.path_cap) path[pn + lane] = (az * g.Y + ay) * g.X + ax;
                             if (last >= 4) via += 1;
                             else if (last < 2) wl += abs(g.xc[ax] - g.xc[bx]);
@@ -402,6 +534,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                 if (lane == dir) {
                     commit_cell(g, d, env, net, cx, cy, cz);
                     *pc = (vc & ~WMASK) | (CF_TREE << 28);
+                    win_mark<C>(cluster, c, cx - wx0, cy - wy0, cz);
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                     if (dir >= 4) via += 1;
                     else if (dir < 2) wl += abs(g.xc[cx] - g.xc[px]);
@@ -419,6 +552,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                         commit_cell(g, d, env, net, cx, cy, cz);
                         uint32_t *pc = win_cell_ptr<C>(cluster, c, H, cx - wx0, cy - wy0, cz);
                         *pc = (*pc & ~WMASK) | (CF_TREE << 28);
+                        win_mark<C>(cluster, c, cx - wx0, cy - wy0, cz);
                     }
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                 }
@@ -469,10 +603,20 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         if (!more) break;
         if (first) {
             // after the first connection only the path is the tree: the unused APs of the
-            // source pin leave the source set
-            for (int i = tid; i < c.Z * c.HH * c.WXp; i += WIN_T) {
-                const uint32_t v = c.cell[i];
-                c.cell[i] = (v & ~WMASK) | (((v >> 28) & CF_TREE) ? 0u : WINF);
+            // source pin leave the source set, so the field is rebuilt from the tree.  With a
+            // single source AP the source set only grew and the old field stays a valid bound.
+            if (n_src_ap > 1) {
+                for (int i = tid; i < c.Z * c.HH * c.WXp; i += WIN_T) {
+                    const uint32_t v = c.cell[i];
+                    const bool tree = ((v >> 28) & CF_TREE) != 0;
+                    c.cell[i] = (v & ~WMASK) | (tree ? 0u : WINF);
+                    if (tree) {
+                        const int x = i % c.WXp, ly = (i / c.WXp) % c.HH, z = i / (c.WXp * c.HH);
+                        if (x < WX && ly >= 1 && ly <= c.h) {
+                            c.rowd[z * H + ly - 1] = 1; c.cold[z * WX + x] = 1; c.posd[(ly - 1) * WX + x] = 1;
+                        }
+                    }
+                }
             }
             first = false;
         }
@@ -483,12 +627,16 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         atomicAdd(&d.dbg[0], (unsigned long long)n_iter); atomicAdd(&d.dbg[1], (unsigned long long)n_conn);
         atomicAdd(&d.dbg[2], (unsigned long long)cyc_relax); atomicAdd(&d.dbg[3], (unsigned long long)(clock64() - tk0));
         atomicAdd(&d.dbg[4], 1ull); atomicAdd(&d.dbg[5], (unsigned long long)(WX * WY));
+#ifdef WIN_PHASE_TIMING
+        for (int k = 0; k < 7; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)ph[k]);
+#endif
     }
-    if (tid == 0) {                                        // every thread counted the same band
-        atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 7]), (unsigned long long)relaxed);
-        if (rank == 0 && band_cells > 0)
-            atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 2]),
-                      (unsigned long long)(relaxed / band_cells));
-    }
+    // relaxation accounting: cells actually touched by the dirty-line sweeps of this band
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) work += __shfl_xor_sync(0xFFFFFFFFu, work, off);
+    if (lane == 0 && work)
+        atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 7]), (unsigned long long)work);
+    if (tid == 0 && rank == 0)
+        atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 2]), (unsigned long long)(3 * n_iter));
     if (C > 1) cluster.sync();                             // keep peers' shared memory alive until all are done
 }

@@ -230,10 +230,11 @@ class VecGame:
         return {"window_nets": a.value, "global_nets": b.value, "window_fallbacks": c.value}
 
     def debug_counters(self) -> dict:
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 16)()
         _lib.check(self._L.xr_debug_counters(self._h, out), self._h)
-        names = ["win_iterations", "win_connections", "win_relax_cycles", "win_kernel_cycles", "win_nets", "win_area"]
-        return {k: int(out[i]) for i, k in enumerate(names)}
+        names = ["win_iterations", "win_connections", "win_relax_cycles", "win_kernel_cycles", "win_nets", "win_area",
+                 "", "", "ph_compact_y", "ph_sweep_y", "ph_compact_x", "ph_sweep_x", "ph_sweep_z", "lines_y", "lines_x"]
+        return {k: int(out[i]) for i, k in enumerate(names) if k}
 
     def profile(self, enable: bool):
         _lib.check(self._L.xr_profile_enable(self._h, int(enable)), self._h)
