@@ -44,8 +44,11 @@ struct XrEnv {
     // window-resident route kernel
     int win_margin = 10, min_cluster = 0, smem_cap = 0, n_sm = 148;
     std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
-    int32_t *p_lists = nullptr;         // pinned [5][N]: mode + env lists of the 4 cluster buckets
-    int32_t *d_lists = nullptr;         // device [4][N]
+    int32_t *p_lists = nullptr;         // pinned [10][N]: mode, group, env lists of the 2 x 4 cluster buckets
+    int32_t *d_lists = nullptr;         // device [8][N]
+    cudaStream_t gs[2] = {nullptr, nullptr};   // one stream per post-route group
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int heavy_pins = 4;                 // nets with at least this many pins form the heavy group
     long long n_win_nets = 0, n_global_nets = 0;
     // counters
     long long n_launch = 0, n_sync = 0;
@@ -126,6 +129,8 @@ static void xr_free(XrEnv *env) {
     if (env->p_flags) cudaFreeHost(env->p_flags);
     if (env->p_ids) cudaFreeHost(env->p_ids);
     if (env->p_lists) cudaFreeHost(env->p_lists);
+    for (int k = 0; k < 2; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
+    if (env->ev_fork) cudaEventDestroy(env->ev_fork);
     for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : env->ev_pool) cudaEventDestroy(e);
     delete env;
@@ -220,7 +225,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(env->d_lists, N * 4); DA(d.dbg, 16);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * 8); DA(d.dbg, 16);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -238,7 +243,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
-        cudaMallocHost(&env->p_lists, sizeof(int32_t) * 5 * N) != cudaSuccess) {
+        cudaMallocHost(&env->p_lists, sizeof(int32_t) * 10 * N) != cudaSuccess) {
         xr_free(env);
         return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
     }
@@ -258,6 +263,11 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     cudaFuncSetAttribute(k_route_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    for (int k = 0; k < 2; k++) {
+        cudaStreamCreateWithFlags(&env->gs[k], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
     // dynamic shared memory of the x+z sweep
     const int smem = g.Z * g.Xp * 5;
     cudaFuncSetAttribute(k_sweep_xz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -388,7 +398,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
 }
 
 // ------------------------------------------------------------------------ obs
-static int launch_obs(XrEnv *env, cudaStream_t st) {
+static int launch_obs(XrEnv *env, cudaStream_t st, int tag = 0) {
     const Geo &g = env->g;
     int maxn = 0;
     for (int i = 0; i < g.N; i++) maxn = std::max(maxn, std::min(env->h_nrem[i], g.obs_max_nets));
@@ -396,7 +406,7 @@ static int launch_obs(XrEnv *env, cudaStream_t st) {
     dim3 grid((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N);
     {
         Launch L(env, XR_K_OBS, st);
-        k_obs<<<grid, OBS_THREADS, 0, st>>>(env->g, env->d);
+        k_obs<<<grid, OBS_THREADS, 0, st>>>(env->g, env->d, tag);
     }
     CK(cudaGetLastError());
     return XR_OK;
@@ -526,7 +536,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     // p_act / p_lists are reused across calls: the previous step's uploads must have completed
     CK(cudaStreamSynchronize(st)); env->n_sync++;
     static const int CS[4] = {1, 2, 4, 8};
-    int nb[4] = {0, 0, 0, 0};
+    int nb[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     int min_cluster = env->min_cluster;
     if (min_cluster == 0) {
         int n_route = 0;
@@ -536,12 +546,14 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         while (min_cluster < 8 && n_route * min_cluster * 2 <= 2 * env->n_sm) min_cluster <<= 1;
     }
     bool any_global = false;
-    int32_t *modes = env->p_lists;                        // [N], then 4 lists of N
+    int n_grp[2] = {0, 0};
+    int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then 8 lists of N: [group][bucket]
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
-        int route = 0, mode = 0;
+        int route = 0, mode = 0, grp = 0;
         if (a >= 1 && env->h_npins[(size_t)i * (g.max_nets + 1) + a] >= 2) {
             route = a; any_route = true;
+            const int np = env->h_npins[(size_t)i * (g.max_nets + 1) + a];
             const int WX = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2];
             const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
             int bucket = -1;
@@ -553,30 +565,61 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
                     if (bytes <= env->smem_cap) bucket = b;
                 }
             }
-            if (bucket >= 0) { mode = 1; env->p_lists[(size_t)(1 + bucket) * g.N + nb[bucket]++] = i; env->n_win_nets++; }
-            else { any_global = true; env->n_global_nets++; }
+            grp = (np >= env->heavy_pins || bucket < 0) ? 1 : 0;
+            if (bucket >= 0) {
+                mode = 1;
+                env->p_lists[(size_t)(2 + grp * 4 + bucket) * g.N + nb[grp][bucket]++] = i;
+                env->n_win_nets++;
+            } else { any_global = true; env->n_global_nets++; }
         }
+        if (a != 0) n_grp[grp]++;
         env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
-        modes[i] = mode;
+        modes[i] = mode; grps[i] = grp;
     }
     CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * 2 * g.N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(env->d.mode, modes, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(env->d.grp, grps, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     if (any_route) {
-        if (nb[0] + nb[1] + nb[2] + nb[3] > 0)
-            CK(cudaMemcpyAsync(env->d_lists, env->p_lists + g.N, sizeof(int32_t) * 4 * g.N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * 8 * g.N, cudaMemcpyHostToDevice, st));
         Launch L(env, XR_K_ROUTE_BEGIN, st);
         k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d);
     }
     { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
     CK(cudaGetLastError());
-    bool need_global = any_global;
-    if (nb[0] + nb[1] + nb[2] + nb[3] > 0) {
+    // ---- the two post-route groups run on their own streams: the light group's metric and
+    // observation kernels (HBM bound) overlap the heavy group's on-chip routing
+    int maxn_grp[2] = {0, 0};
+    for (int i = 0; i < g.N; i++) {
+        if (actions[i] == 0) continue;
+        const int after = env->h_nrem[i] - (actions[i] >= 1 ? 1 : 0);
+        maxn_grp[grps[i]] = std::max(maxn_grp[grps[i]], std::min(after, g.obs_max_nets));
+    }
+    const bool split = n_grp[0] > 0 && n_grp[1] > 0 && any_route;
+    if (split) CK(cudaEventRecord(env->ev_fork, st));
+    for (int grp = 0; grp < 2; grp++) {
+        const bool has = n_grp[grp] > 0;
+        if (!has && grp == 1) continue;                   // (group 0 always runs: it also finalises idle envs)
+        cudaStream_t sg = split ? env->gs[grp] : st;
+        if (split) CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
         for (int b = 0; b < 4; b++) {
-            if (!nb[b]) continue;
-            int rc = launch_route_win(env, st, CS[b], nb[b], env->d_lists + (size_t)b * g.N);
+            if (!nb[grp][b]) continue;
+            int rc = launch_route_win(env, sg, CS[b], nb[grp][b], env->d_lists + (size_t)(grp * 4 + b) * g.N);
             if (rc != XR_OK) return rc;
         }
-        // did any window search hand its environment over to the full-grid path?
+        if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
+        { Launch L(env, XR_K_MISC, sg); k_finalize<<<(g.N + 127) / 128, 128, 0, sg>>>(env->g, env->d, grp); }
+        if (has) {
+            const long long total = (2ll + 7ll * maxn_grp[grp]) * g.cells;
+            Launch L(env, XR_K_OBS, sg);
+            k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, sg>>>(env->g, env->d, grp + 2);
+        }
+        if (split) { CK(cudaEventRecord(env->ev_join[grp], sg)); CK(cudaStreamWaitEvent(st, env->ev_join[grp], 0)); }
+    }
+    CK(cudaGetLastError());
+    // ---- environments whose window search escaped, or whose window does not fit on chip,
+    // are routed by the full-grid sweeps and finalised in a last pass
+    bool need_global = any_global;
+    if (any_route && !need_global) {
         CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st)); env->n_sync++;
         if (env->p_flags[1] != 0) {
@@ -604,12 +647,16 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (env->p_flags[0] == 0) break;
             if (pumps > guard * 64) return fail(env, XR_E_UNROUTABLE, "maze search did not converge");
         }
+        { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -1); }
+        { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -1); }
+        {
+            int maxn = std::max(maxn_grp[0], maxn_grp[1]);
+            const long long total = (2ll + 7ll * maxn) * g.cells;
+            Launch L(env, XR_K_OBS, st);
+            k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, st>>>(env->g, env->d, 1);
+        }
+        CK(cudaGetLastError());
     }
-    if (any_act) {
-        { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d); }
-    }
-    { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d); }
-    CK(cudaGetLastError());
     // ---- host mirror
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
@@ -619,7 +666,6 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (env->h_nrem[i] == 0) env->h_done[i] = 1;
         } else if (a == -1) env->h_done[i] = 1;
     }
-    if (any_act) return launch_obs(env, st);
     return XR_OK;
 }
 
@@ -962,7 +1008,7 @@ extern "C" int xr_build_obs_from_nodes(int32_t device, int32_t X, int32_t Y, int
     cudaMemcpyAsync(d.net_start, ns2.data(), sizeof(int32_t) * (g.max_nets + 2), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d.ap_obsoff, obsoff.data(), sizeof(int32_t) * g.max_aps, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d.ap_adj, adj.data(), g.max_aps, cudaMemcpyHostToDevice, st);
-    k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), 1), OBS_THREADS, 0, st>>>(g, d);
+    k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), 1), OBS_THREADS, 0, st>>>(g, d, 0);
     cudaMemcpyAsync(host_out, d.obs, sizeof(float) * total, cudaMemcpyDeviceToHost, st);
     ce = cudaStreamSynchronize(st);
     freeall();

@@ -66,6 +66,8 @@ struct Dev {
     uint8_t  *cflag;      // [N][cells_p]
     int32_t  *act;        // [N][2] raw action, net to route (0 = none)
     int32_t  *mode;       // [N] 0 = global full-grid sweeps, 1 = window-resident kernel
+    int32_t  *grp;        // [N] post-route group (0 light, 1 heavy): groups finish on their own streams
+    int32_t  *fin;        // [N] 0 = step epilogue pending, else tag of the pass that finalised the env
     int32_t  *phase;      // [N] 0 idle, 1 routing
     int32_t  *changed;    // [N]
     int32_t  *reinit;     // [N]

@@ -10,6 +10,15 @@
 // with 16-byte stores (channel 0 from the obstacle bytes, channel 1 from the rank
 // list, net channels zero) and, after a block barrier, patches the access points
 // that fall inside its chunk.  Algorithmic bytes: 4*(2+7n)*cells written per env.
+// Which environments a step-epilogue pass covers.  pass >= 0: the environments of post-route
+// group `pass` whose route is complete (phase 0) and that no earlier pass finalised;
+// pass < 0: everything still pending (after the full-grid route loop).  Tag = pass + 2 / 1.
+__device__ __forceinline__ bool pass_selects(const Dev &d, int env, int pass) {
+    if (d.fin[env] != 0) return false;
+    return pass < 0 || (d.grp[env] == pass && d.phase[env] == 0);
+}
+__device__ __forceinline__ int pass_tag(int pass) { return pass < 0 ? 1 : pass + 2; }
+
 #define OBS_THREADS 256
 #define OBS_F4_PER_THREAD 16
 #define OBS_CHUNK (OBS_THREADS * OBS_F4_PER_THREAD * 4)   // floats per CTA (64 KB)
@@ -19,9 +28,9 @@ __device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
                  : "memory");
 }
 
-__global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d) {
+__global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d, int tag) {
     const int env = blockIdx.y;
-    if (!d.obs_do[env]) return;
+    if (!d.obs_do[env] || (tag != 0 && d.fin[env] != tag)) return;
     const int n_rem = d.n_remaining[env];
     const int n = n_rem < g.obs_max_nets ? n_rem : g.obs_max_nets;
     const long long cells = g.cells;
@@ -86,9 +95,9 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d) {
 // on a pin), overflow (sum of usage beyond capacity 1).  Stands in for the
 // simulator-side Request.reward_violation (net_ordering.proto:37).  Reads 4 bytes
 // per cell (cellinfo); apnet only for occupied AP cells.
-__global__ void __launch_bounds__(256) k_metrics(Geo g, Dev d) {
+__global__ void __launch_bounds__(256) k_metrics(Geo g, Dev d, int pass) {
     const int env = blockIdx.y;
-    if (d.act[2 * env] < 1) return;
+    if (d.act[2 * env] < 1 || !pass_selects(d, env, pass)) return;
     const size_t eoff = (size_t)env * g.cells_p;
     const uint4 *ci4 = reinterpret_cast<const uint4 *>(d.cellinfo + eoff);
     const int n4 = g.cells_p >> 2;
@@ -144,9 +153,10 @@ __device__ void refresh_remaining(const Geo &g, const Dev &d, int env) {
 
 // Per-step epilogue (baseline_utils.py:426-438): metric deltas, done flag, reward
 // (train_PPO.py:101-102), remaining-net list for the order channel.
-__global__ void k_finalize(Geo g, Dev d) {
+__global__ void k_finalize(Geo g, Dev d, int pass) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= g.N) return;
+    if (env >= g.N || !pass_selects(d, env, pass)) return;
+    d.fin[env] = pass_tag(pass);
     const int raw = d.act[2 * env];
     if (raw < 1) {
         d.delta[3 * env] = 0; d.delta[3 * env + 1] = 0; d.delta[3 * env + 2] = 0;

@@ -59,6 +59,7 @@ __global__ void k_seed(Geo g, Dev d) {
     const int raw = d.act[2 * env], net = d.act[2 * env + 1];
     if (threadIdx.x == 0) {
         d.obs_do[env] = (raw != 0);
+        d.fin[env] = 0;
         if (raw >= 1) d.routed[(size_t)env * (g.max_nets + 1) + raw] = 1;
         if (raw == -1) d.done[env] = 1;
         d.path_n[env] = 0; d.conn_n[env] = 0;
