@@ -168,6 +168,9 @@ int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, in
 /* Window-kernel diagnostics, uint64 [16] ([8..14] per-phase cycles when built with -DWIN_PHASE_TIMING): iterations, connections, relax cycles, kernel
  * cycles (rank-0 CTAs), nets, sum of window areas (cells per layer).                  */
 int xr_debug_counters(XrEnv *env, uint64_t *out);
+/* Profiling timeline, double [6]: per post-route group mean ms offsets from step start of
+ * route start, route end, observation end (needs xr_profile_enable).                 */
+int xr_debug_timeline(XrEnv *env, double *out);
 
 /* Per-kernel-class device timing with CUDA events on the launching stream.
  * enable: 0/1.  xr_profile_get synchronises and returns accumulated milliseconds

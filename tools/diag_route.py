@@ -24,8 +24,10 @@ for kw in settings:
         if t % N_NETS == 0:
             vg.reset()
         vg.step(sched[t])
+    tl = vg.debug_timeline()
     prof = vg.profile_get()
     print(kw, "ms/step mean %.2f median %.2f max %.2f" % (1e3*np.mean(ts), 1e3*np.median(ts), 1e3*np.max(ts)),
           vg.route_counters(), vg.counters(), vg.debug_counters())
     print("   ", {k: (round(v["ms"],1), v["launches"]) for k, v in prof.items() if v["launches"]})
+    print("    timeline(ms from step start):", tl)
     vg.close()

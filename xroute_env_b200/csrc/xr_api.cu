@@ -15,13 +15,14 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 static std::string g_create_error;
 
-struct ProfEvent { int cls; cudaEvent_t a, b; };
+struct ProfEvent { int cls; cudaEvent_t a, b; cudaEvent_t step; int grp; };
 
 struct XrEnv {
     XrConfig cfg;
@@ -49,6 +50,7 @@ struct XrEnv {
     cudaStream_t gs[2] = {nullptr, nullptr};   // one stream per post-route group
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int heavy_pins = 4;                 // nets with at least this many pins form the heavy group
+    int heavy_cluster = 0;              // minimum cluster size of the heavy group (0 = same as the light group)
     long long n_win_nets = 0, n_global_nets = 0;
     // counters
     long long n_launch = 0, n_sync = 0;
@@ -57,6 +59,11 @@ struct XrEnv {
     std::vector<ProfEvent> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
     double prof_ms[XR_K_COUNT] = {0};
+    cudaEvent_t cur_step_ev = nullptr;  // start of the current step (profiling timeline)
+    int cur_grp = -1;
+    std::vector<cudaEvent_t> step_evs;
+    double tl_sum[2][3] = {{0, 0, 0}, {0, 0, 0}};   // per group: route start / route end / obs end offsets (ms)
+    long long tl_n[2][3] = {{0, 0, 0}, {0, 0, 0}};
     long long prof_n[XR_K_COUNT] = {0};
     std::atomic<int> refs{1};           // handle + outstanding DLPack tensors
 };
@@ -101,7 +108,7 @@ struct Launch {
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
     ~Launch() {
-        if (env->prof) { cudaEventRecord(b, st); env->prof_pending.push_back({cls, a, b}); }
+        if (env->prof) { cudaEventRecord(b, st); env->prof_pending.push_back({cls, a, b, env->cur_step_ev, env->cur_grp}); }
     }
 };
 
@@ -110,9 +117,21 @@ static void prof_collect(XrEnv *env) {
         float ms = 0.f;
         cudaEventSynchronize(p.b);
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { env->prof_ms[p.cls] += ms; env->prof_n[p.cls]++; }
+        if (p.step && p.grp >= 0 && p.grp < 2 && (p.cls == XR_K_ROUTE_WIN || p.cls == XR_K_OBS)) {
+            float o0 = 0.f, o1 = 0.f;
+            if (cudaEventElapsedTime(&o0, p.step, p.a) == cudaSuccess && cudaEventElapsedTime(&o1, p.step, p.b) == cudaSuccess) {
+                if (p.cls == XR_K_ROUTE_WIN) {
+                    env->tl_sum[p.grp][0] += o0; env->tl_n[p.grp][0]++;
+                    env->tl_sum[p.grp][1] += o1; env->tl_n[p.grp][1]++;
+                } else { env->tl_sum[p.grp][2] += o1; env->tl_n[p.grp][2]++; }
+            }
+        }
         env->ev_pool.push_back(p.a); env->ev_pool.push_back(p.b);
     }
     env->prof_pending.clear();
+    for (auto e : env->step_evs) env->ev_pool.push_back(e);
+    env->step_evs.clear();
+    env->cur_step_ev = nullptr;
 }
 
 // ----------------------------------------------------------------- create/destroy
@@ -268,6 +287,9 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
+    // tuning knobs (not part of the ABI): XR_HEAVY_PINS, XR_HEAVY_CLUSTER
+    if (const char *e = getenv("XR_HEAVY_PINS")) env->heavy_pins = std::max(2, atoi(e));
+    if (const char *e = getenv("XR_HEAVY_CLUSTER")) env->heavy_cluster = atoi(e);
     // dynamic shared memory of the x+z sweep
     const int smem = g.Z * g.Xp * 5;
     cudaFuncSetAttribute(k_sweep_xz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -535,6 +557,13 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     }
     // p_act / p_lists are reused across calls: the previous step's uploads must have completed
     CK(cudaStreamSynchronize(st)); env->n_sync++;
+    env->cur_grp = -1;
+    if (env->prof) {
+        cudaEvent_t e;
+        if (!env->ev_pool.empty()) { e = env->ev_pool.back(); env->ev_pool.pop_back(); } else cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        env->cur_step_ev = e; env->step_evs.push_back(e);
+    }
     static const int CS[4] = {1, 2, 4, 8};
     int nb[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     int min_cluster = env->min_cluster;
@@ -557,9 +586,10 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             const int WX = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2];
             const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
             int bucket = -1;
+            const int mc = (np >= env->heavy_pins && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
             if (WX > 0) {
                 for (int b = 0; b < 4 && bucket < 0; b++) {
-                    if (CS[b] < min_cluster) continue;
+                    if (CS[b] < mc) continue;
                     const int H = (WY + CS[b] - 1) / CS[b];
                     const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX));
                     if (bytes <= env->smem_cap) bucket = b;
@@ -600,6 +630,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         const bool has = n_grp[grp] > 0;
         if (!has && grp == 1) continue;                   // (group 0 always runs: it also finalises idle envs)
         cudaStream_t sg = split ? env->gs[grp] : st;
+        env->cur_grp = grp;
         if (split) CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
         for (int b = 0; b < 4; b++) {
             if (!nb[grp][b]) continue;
@@ -616,6 +647,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         if (split) { CK(cudaEventRecord(env->ev_join[grp], sg)); CK(cudaStreamWaitEvent(st, env->ev_join[grp], 0)); }
     }
     CK(cudaGetLastError());
+    env->cur_grp = -1;
     // ---- environments whose window search escaped, or whose window does not fit on chip,
     // are routed by the full-grid sweeps and finalised in a last pass
     bool need_global = any_global;
@@ -888,6 +920,22 @@ extern "C" int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *glob
     if (window_nets) *window_nets = env->n_win_nets;
     if (global_nets) *global_nets = env->n_global_nets;
     if (window_fallbacks) *window_fallbacks = fb;
+    return XR_OK;
+}
+
+/* Profiling timeline (needs xr_profile_enable): mean offsets in ms from the start of a step
+ * of, per post-route group g: out[3g+0] first route launch start, [3g+1] route end,
+ * [3g+2] observation end.  Cleared on read.                                          */
+extern "C" int xr_debug_timeline(XrEnv *env, double *out) {
+    if (!env || !out) return XR_E_INVALID;
+    cudaSetDevice(env->device);
+    cudaDeviceSynchronize();
+    prof_collect(env);
+    for (int gidx = 0; gidx < 2; gidx++)
+        for (int k = 0; k < 3; k++) {
+            out[3 * gidx + k] = env->tl_n[gidx][k] ? env->tl_sum[gidx][k] / env->tl_n[gidx][k] : 0.0;
+            env->tl_sum[gidx][k] = 0; env->tl_n[gidx][k] = 0;
+        }
     return XR_OK;
 }
 

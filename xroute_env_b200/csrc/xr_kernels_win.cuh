@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 // words of shared memory besides the cells: tables, target list, dirty flags, work list
 #define WIN_AUX_WORDS(Z, H, WX)                                                                   \
     (3 * (Z) + 3 * (Z) + 24 * (Z) + (WX) + 2 + (H) + 4 + 64 + 2 * WIN_TGT_CAP +                                \
-     ((Z) * (H) + (Z) * (WX) + (H) * (WX)) / 4 + 3 + ((Z) * ((H) > (WX) ? (H) : (WX))) / 2 + 2)
+     ((Z) * (H) + (Z) * (WX) + (H) * (WX)) / 4 + 3 + ((Z) * ((H) > (WX) ? (H) : (WX))) / 2 + 2 + WIN_TGT_CAP + 8)
 
 struct WinCtx {
     uint32_t *cell;      // [Z][HH][WXp]
@@ -83,11 +83,11 @@ __device__ int win_compact(const WinCtx &c, uint8_t *flags, int n) {
 // many lines are dirty (throughput bound: fewest instructions per cell).
 #define WIN_BATCH 8
 template <int DIR, bool UNI>
-__device__ __forceinline__ bool win_walk(uint32_t *__restrict__ p, int n, int stride, uint32_t t, uint32_t lutreg,
-                                         uint32_t pen, const uint32_t *__restrict__ len,
-                                         const uint32_t *__restrict__ wl,
-                                         uint8_t *__restrict__ fa, int sa, uint8_t *__restrict__ fb, int sb) {
-    bool ch = false;
+__device__ __forceinline__ uint32_t win_walk(uint32_t *__restrict__ p, int n, int stride, uint32_t t, uint32_t lutreg,
+                                             uint32_t pen, const uint32_t *__restrict__ len,
+                                             const uint32_t *__restrict__ wl,
+                                             uint8_t *__restrict__ fa, int sa, uint8_t *__restrict__ fb, int sb) {
+    uint32_t ch = 0xFFFFFFFFu;           // smallest distance written (0xFFFFFFFF = nothing changed)
     for (int i0 = 0; i0 < n; i0 += WIN_BATCH) {
         uint32_t v[WIN_BATCH], w[WIN_BATCH];
 #pragma unroll
@@ -106,7 +106,7 @@ __device__ __forceinline__ bool win_walk(uint32_t *__restrict__ p, int n, int st
                 const int i = DIR > 0 ? j : n - 1 - j;
                 const uint32_t dcur = v[k] & WMASK;
                 const uint32_t nd = xr_min(t + w[k], dcur);
-                if (nd < dcur) { p[i * stride] = (v[k] & ~WMASK) | nd; fa[i * sa] = 1; fb[i * sb] = 1; ch = true; }
+                if (nd < dcur) { p[i * stride] = (v[k] & ~WMASK) | nd; fa[i * sa] = 1; fb[i * sb] = 1; ch = xr_min(ch, nd); }
                 t = nd;
             }
         }
@@ -115,8 +115,8 @@ __device__ __forceinline__ bool win_walk(uint32_t *__restrict__ p, int n, int st
 }
 
 // one thread per dirty (z, x) column of the band: forward from the upper halo, back from the lower
-__device__ bool win_sweep_y(const WinCtx &c, int n, long long &work) {
-    bool ch = false;
+__device__ uint32_t win_sweep_y(const WinCtx &c, int n, long long &work) {
+    uint32_t ch = 0xFFFFFFFFu;
     for (int k = threadIdx.x; k < n; k += WIN_T) {
         const int col = c.list[k];
         const int z = col / c.WX, x = col - z * c.WX;
@@ -124,15 +124,15 @@ __device__ bool win_sweep_y(const WinCtx &c, int n, long long &work) {
         const uint32_t lutreg = c.lutm[1 * c.Z + z], pen = c.pens[z];
         const uint32_t *wl = c.wlut + (1 * c.Z + z) * 8;
         if (c.uni_y) {
-            ch |= win_walk<1, true>(p + c.WXp, c.h, c.WXp, p[0] & WMASK, lutreg, pen, c.leny + 1, wl,
-                                    c.rowd + z * c.H, 1, c.posd + x, c.WX);
-            ch |= win_walk<-1, true>(p + c.WXp, c.h, c.WXp, p[(c.h + 1) * c.WXp] & WMASK, lutreg, pen, c.leny + 1, wl,
-                                     c.rowd + z * c.H, 1, c.posd + x, c.WX);
+            ch = xr_min(ch, win_walk<1, true>(p + c.WXp, c.h, c.WXp, p[0] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                    c.rowd + z * c.H, 1, c.posd + x, c.WX));
+            ch = xr_min(ch, win_walk<-1, true>(p + c.WXp, c.h, c.WXp, p[(c.h + 1) * c.WXp] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                     c.rowd + z * c.H, 1, c.posd + x, c.WX));
         } else {
-            ch |= win_walk<1, false>(p + c.WXp, c.h, c.WXp, p[0] & WMASK, lutreg, pen, c.leny + 1, wl,
-                                     c.rowd + z * c.H, 1, c.posd + x, c.WX);
-            ch |= win_walk<-1, false>(p + c.WXp, c.h, c.WXp, p[(c.h + 1) * c.WXp] & WMASK, lutreg, pen, c.leny + 1, wl,
-                                      c.rowd + z * c.H, 1, c.posd + x, c.WX);
+            ch = xr_min(ch, win_walk<1, false>(p + c.WXp, c.h, c.WXp, p[0] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                     c.rowd + z * c.H, 1, c.posd + x, c.WX));
+            ch = xr_min(ch, win_walk<-1, false>(p + c.WXp, c.h, c.WXp, p[(c.h + 1) * c.WXp] & WMASK, lutreg, pen, c.leny + 1, wl,
+                                      c.rowd + z * c.H, 1, c.posd + x, c.WX));
         }
         work += c.h;
     }
@@ -140,8 +140,8 @@ __device__ bool win_sweep_y(const WinCtx &c, int n, long long &work) {
 }
 
 // one thread per dirty (z, ly) row of the band
-__device__ bool win_sweep_x(const WinCtx &c, int n, long long &work) {
-    bool ch = false;
+__device__ uint32_t win_sweep_x(const WinCtx &c, int n, long long &work) {
+    uint32_t ch = 0xFFFFFFFFu;
     for (int k = threadIdx.x; k < n; k += WIN_T) {
         const int row = c.list[k];
         const int z = row / c.H, ly = row - z * c.H + 1;
@@ -149,11 +149,11 @@ __device__ bool win_sweep_x(const WinCtx &c, int n, long long &work) {
         const uint32_t lutreg = c.lutm[0 * c.Z + z], pen = c.pens[z];
         const uint32_t *wl = c.wlut + (0 * c.Z + z) * 8;
         if (c.uni_x) {
-            ch |= win_walk<1, true>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
-            ch |= win_walk<-1, true>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
+            ch = xr_min(ch, win_walk<1, true>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1));
+            ch = xr_min(ch, win_walk<-1, true>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1));
         } else {
-            ch |= win_walk<1, false>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
-            ch |= win_walk<-1, false>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1);
+            ch = xr_min(ch, win_walk<1, false>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1));
+            ch = xr_min(ch, win_walk<-1, false>(p, c.WX, 1, WINF, lutreg, pen, c.lenx, wl, c.cold + z * c.WX, 1, c.posd + (ly - 1) * c.WX, 1));
         }
         work += c.WX;
     }
@@ -162,8 +162,8 @@ __device__ bool win_sweep_x(const WinCtx &c, int n, long long &work) {
 
 // one thread per (ly, x) position whose via stack is dirty: up then down through the layers
 // (the Z cells are fetched first so their shared-memory latency overlaps)
-__device__ bool win_sweep_z(const WinCtx &c, long long &work) {
-    bool ch = false;
+__device__ uint32_t win_sweep_z(const WinCtx &c, long long &work) {
+    uint32_t ch = 0xFFFFFFFFu;
     const int npos = c.WX * c.h;
     const size_t zs = (size_t)c.HH * c.WXp;
     const uint32_t lutreg = c.lutm[2 * c.Z];
@@ -181,13 +181,13 @@ __device__ bool win_sweep_z(const WinCtx &c, long long &work) {
         for (int z = 1; z < XR_ZMAX; z++) if (z < c.Z) {
             const uint32_t dcur = v[z] & WMASK;
             t = xr_min(t + win_w(lutreg, c.pens[z], c.pens[c.Z + z], v[z]), dcur);
-            if (t < dcur) { v[z] = (v[z] & ~WMASK) | t; chg |= 1u << z; }
+            if (t < dcur) { v[z] = (v[z] & ~WMASK) | t; chg |= 1u << z; ch = xr_min(ch, t); }
         }
 #pragma unroll
         for (int z = XR_ZMAX - 2; z >= 0; z--) if (z < c.Z - 1) {
             const uint32_t dcur = v[z] & WMASK;
             t = xr_min(t + win_w(lutreg, c.pens[z], c.pens[2 * c.Z + z], v[z]), dcur);
-            if (t < dcur) { v[z] = (v[z] & ~WMASK) | t; chg |= 1u << z; }
+            if (t < dcur) { v[z] = (v[z] & ~WMASK) | t; chg |= 1u << z; ch = xr_min(ch, t); }
         }
         if (chg) {
 #pragma unroll
@@ -195,7 +195,6 @@ __device__ bool win_sweep_z(const WinCtx &c, long long &work) {
                 p[z * zs] = v[z];
                 c.rowd[z * c.H + lyi] = 1; c.cold[z * c.WX + x] = 1;
             }
-            ch = true;
         }
         work += c.Z;
     }
@@ -249,6 +248,8 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     unsigned long long *s_best = reinterpret_cast<unsigned long long *>(aux); aux += 4;
     int *s_flag = reinterpret_cast<int *>(aux); aux += 8;   // [0..1] changed (double buffered), [2] exit, [3] more, [4] #targets, [5] list count
     int *s_tgt = reinterpret_cast<int *>(aux); aux += 2 * WIN_TGT_CAP;   // DBU coordinates of the unconnected APs
+    uint32_t *s_tloc = aux; aux += WIN_TGT_CAP;             // cell index of the unconnected APs inside this band
+    uint32_t *s_red = aux; aux += 8;                        // [parity][0] smallest distance written, [1] best target in band, [4] #local targets
     c.cnt = &s_flag[5];
     c.rowd = reinterpret_cast<uint8_t *>(aux);
     c.cold = c.rowd + c.Z * H;
@@ -320,10 +321,36 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     if (C > 1) cluster.sync(); else __syncthreads();
     const int n_src_ap = s_flag[6];
     for (;;) {                                            // ---- one connection per trip
-        // ---- relax to the fixpoint
+        // ---- targets of this connection: every AP of every unconnected pin.  All CTAs keep
+        // the DBU coordinates (exit-test heuristic); each keeps the cells inside its band.
+        if (tid == 0) { s_flag[4] = 0; s_red[4] = 0; }
+        __syncthreads();
+        for (int i = s + tid; i < t; i += WIN_T) {
+            if (d.ap_conn[aoff + i]) continue;
+            const int cp = d.ap_cellp[aoff + i];
+            const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
+            const int k = atomicAdd(&s_flag[4], 1);
+            if (k < WIN_TGT_CAP) { s_tgt[2 * k] = g.xc[gx]; s_tgt[2 * k + 1] = g.yc[gy]; }
+            const int ly = gy - wy0 - c.ry0 + 1;
+            if (ly >= 1 && ly <= c.h) {
+                const unsigned m = atomicAdd(&s_red[4], 1u);
+                if (m < WIN_TGT_CAP) s_tloc[m] = (uint32_t)(((size_t)z * c.HH + ly) * c.WXp + (gx - wx0));
+            }
+        }
+        __syncthreads();
+        const int n_tgt = s_flag[4];
+        const int n_loc = (int)s_red[4];
+        const bool early = n_tgt <= WIN_TGT_CAP;          // bounded stop needs the complete target list
+        // ---- relax until nothing below the best target distance can change any more.
+        // A sweep only ever writes values >= the value it propagates from, so once every
+        // distance written in an iteration is >= B (the best target distance), all cells
+        // with distance < B -- everything the target choice, the exit test and the backtrace
+        // read -- are final.  The remaining dirty lines stay flagged and are folded into
+        // the next connection's iterations (or dropped when the net is done).
         const long long tr0 = clock64();
         for (;;) {
             n_iter++;
+            if (tid == 0) { s_red[2 * parity] = 0xFFFFFFFFu; s_red[2 * parity + 1] = 0xFFFFFFFFu; }
             if (C > 1) {
                 // pull the neighbours' boundary rows into the halo rows
                 for (int i = tid; i < 2 * c.Z * WX; i += WIN_T) {
@@ -349,7 +376,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
 #ifdef WIN_PHASE_TIMING
             const long long p1 = clock64();
 #endif
-            bool ch = win_sweep_y(c, ny, work);
+            uint32_t ch = win_sweep_y(c, ny, work);
 #ifdef WIN_PHASE_TIMING
             __syncthreads();
             const long long p2 = clock64();
@@ -358,41 +385,47 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
 #ifdef WIN_PHASE_TIMING
             const long long p3 = clock64();
 #endif
-            ch |= win_sweep_x(c, nx, work);
+            ch = xr_min(ch, win_sweep_x(c, nx, work));
             __syncthreads();
 #ifdef WIN_PHASE_TIMING
             const long long p4 = clock64();
 #endif
-            ch |= win_sweep_z(c, work);
-            const int anyc = __syncthreads_or(ch);
+            ch = xr_min(ch, win_sweep_z(c, work));
+            ch = __reduce_min_sync(0xFFFFFFFFu, ch);
+            if (lane == 0 && ch != 0xFFFFFFFFu) atomicMin(&s_red[2 * parity], ch);
+            __syncthreads();                              // via sweep done: target cells are current
+            if (early) {
+                uint32_t bl = 0xFFFFFFFFu;
+                for (int k = tid; k < n_loc; k += WIN_T) bl = xr_min(bl, c.cell[s_tloc[k]] & WMASK);
+                bl = __reduce_min_sync(0xFFFFFFFFu, bl);
+                if (lane == 0 && bl != 0xFFFFFFFFu) atomicMin(&s_red[2 * parity + 1], bl);
+            }
 #ifdef WIN_PHASE_TIMING
             const long long p5 = clock64();
             ph[0] += p1 - p0; ph[1] += p2 - p1; ph[2] += p3 - p2; ph[3] += p4 - p3; ph[4] += p5 - p4;
             ph[5] += ny; ph[6] += nx;
 #endif
-            if (C > 1) {
-                if (tid == 0) s_flag[parity] = anyc;
-                cluster.sync();
-                int tot = 0;
-                for (int r = 0; r < C; r++) tot |= *cluster.map_shared_rank(&s_flag[parity], r);
-                parity ^= 1;
-                if (!tot) break;
-            } else if (!anyc) break;
+            if (C > 1) cluster.sync(); else __syncthreads();
+            uint32_t gmin = 0xFFFFFFFFu, gB = 0xFFFFFFFFu;
+            for (int r = 0; r < C; r++) {
+                const uint32_t *rr = (C > 1) ? cluster.map_shared_rank(&s_red[2 * parity], r) : &s_red[2 * parity];
+                gmin = xr_min(gmin, rr[0]); gB = xr_min(gB, rr[1]);
+            }
+            parity ^= 1;
+            if (gmin == 0xFFFFFFFFu) break;               // fixpoint
+            if (early && gB < WINF && gmin >= gB) break;  // nothing relevant can change any more
         }
         // ---- best target in this band + window-exit test
         const long long tq0 = clock64();
         cyc_relax += tq0 - tr0; n_conn++;
-        if (tid == 0) { s_best[0] = ~0ull; s_flag[4] = 0; }
+        if (tid == 0) s_best[0] = ~0ull;
         __syncthreads();
         unsigned long long best = ~0ull;
         for (int i = s + tid; i < t; i += WIN_T) {
             if (d.ap_conn[aoff + i]) continue;
             const int cp = d.ap_cellp[aoff + i];
             const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
-            const int k = atomicAdd(&s_flag[4], 1);          // every CTA keeps the full target list
-            if (k < WIN_TGT_CAP) { s_tgt[2 * k] = g.xc[gx]; s_tgt[2 * k + 1] = g.yc[gy]; }
-            const int x = gx - wx0, wy = gy - wy0;
-            const int ly = wy - c.ry0 + 1;
+            const int x = gx - wx0, ly = gy - wy0 - c.ry0 + 1;
             if (ly < 1 || ly > c.h) continue;
             const uint32_t dv = c.cell[((size_t)z * c.HH + ly) * c.WXp + x] & WMASK;
             const unsigned long long key = ((unsigned long long)dv << 32) | (unsigned)cp;
@@ -410,7 +443,6 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
             const unsigned long long o = (C > 1) ? *cluster.map_shared_rank(&s_best[0], r) : s_best[0];
             best = o < best ? o : best;
         }
-        const int n_tgt = s_flag[4];
         const uint32_t B = (uint32_t)(best >> 32);
         // exit test over the open faces of the band
         bool esc = (best == ~0ull) || B >= WINF;

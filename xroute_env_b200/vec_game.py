@@ -236,6 +236,12 @@ class VecGame:
                  "", "", "ph_compact_y", "ph_sweep_y", "ph_compact_x", "ph_sweep_x", "ph_sweep_z", "lines_y", "lines_x"]
         return {k: int(out[i]) for i, k in enumerate(names) if k}
 
+    def debug_timeline(self) -> dict:
+        out = (C.c_double * 6)()
+        _lib.check(self._L.xr_debug_timeline(self._h, out), self._h)
+        return {f"g{g}_{n}": round(out[3 * g + k], 3) for g in range(2)
+                for k, n in enumerate(("route_start", "route_end", "obs_end"))}
+
     def profile(self, enable: bool):
         _lib.check(self._L.xr_profile_enable(self._h, int(enable)), self._h)
 
