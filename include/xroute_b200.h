@@ -73,7 +73,7 @@ typedef struct XrConfig {
     int32_t via_cost, grid_cost, drc_cost, fixed_shape_cost, block_cost; /* router constants */
     int32_t pumps_per_sync;    /* relaxation iterations launched between host polls; 0 = default */
     int32_t window_margin;     /* cells added around a net's AP bounding box for the on-chip window
-                                  search; 0 = default (10), <0 = always use the full-grid sweeps  */
+                                  search; 0 = default (14), <0 = always use the full-grid sweeps  */
     int32_t min_cluster;       /* smallest CTA cluster per environment for the window kernel
                                   (1, 2, 4 or 8); 0 = auto (from the number of routing environments) */
     int32_t reserved[5];
@@ -168,7 +168,7 @@ int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, in
 /* Window-kernel diagnostics, uint64 [16] ([8..14] per-phase cycles when built with -DWIN_PHASE_TIMING): iterations, connections, relax cycles, kernel
  * cycles (rank-0 CTAs), nets, sum of window areas (cells per layer).                  */
 int xr_debug_counters(XrEnv *env, uint64_t *out);
-/* Profiling timeline, double [6]: per post-route group mean ms offsets from step start of
+/* Profiling timeline, double [9]: per post-route group (3) mean ms offsets from step start of
  * route start, route end, observation end (needs xr_profile_enable).                 */
 int xr_debug_timeline(XrEnv *env, double *out);
 

@@ -22,6 +22,7 @@
 
 static std::string g_create_error;
 
+#define XR_NG 3   // post-route groups
 struct ProfEvent { int cls; cudaEvent_t a, b; cudaEvent_t step; int grp; };
 
 struct XrEnv {
@@ -43,14 +44,14 @@ struct XrEnv {
     int32_t *d_ids = nullptr;
     int pumps_per_sync = 4;
     // window-resident route kernel
-    int win_margin = 10, min_cluster = 0, smem_cap = 0, n_sm = 148;
+    int win_margin = 14, min_cluster = 0, smem_cap = 0, n_sm = 148;
     std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
-    int32_t *p_lists = nullptr;         // pinned [10][N]: mode, group, env lists of the 2 x 4 cluster buckets
-    int32_t *d_lists = nullptr;         // device [8][N]
-    cudaStream_t gs[2] = {nullptr, nullptr};   // one stream per post-route group
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    int heavy_pins = 4;                 // nets with at least this many pins form the heavy group
-    int heavy_cluster = 0;              // minimum cluster size of the heavy group (0 = same as the light group)
+    int32_t *p_lists = nullptr;         // pinned [2 + 4*XR_NG][N]: mode, group, env lists of the XR_NG x 4 cluster buckets
+    int32_t *d_lists = nullptr;         // device [4*XR_NG][N]
+    cudaStream_t gs[XR_NG] = {nullptr, nullptr, nullptr};   // one stream per post-route group
+    cudaEvent_t ev_fork = nullptr, ev_join[XR_NG] = {nullptr, nullptr, nullptr};
+    int grp_pins[XR_NG] = {0, 4, 8};    // group g = nets with at least grp_pins[g] pins (light / medium / heavy)
+    int heavy_cluster = 8;              // minimum cluster size of the heaviest group (0 = same as the others)
     long long n_win_nets = 0, n_global_nets = 0;
     // counters
     long long n_launch = 0, n_sync = 0;
@@ -62,8 +63,8 @@ struct XrEnv {
     cudaEvent_t cur_step_ev = nullptr;  // start of the current step (profiling timeline)
     int cur_grp = -1;
     std::vector<cudaEvent_t> step_evs;
-    double tl_sum[2][3] = {{0, 0, 0}, {0, 0, 0}};   // per group: route start / route end / obs end offsets (ms)
-    long long tl_n[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    double tl_sum[XR_NG][3] = {};   // per group: route start / route end / obs end offsets (ms)
+    long long tl_n[XR_NG][3] = {};
     long long prof_n[XR_K_COUNT] = {0};
     std::atomic<int> refs{1};           // handle + outstanding DLPack tensors
 };
@@ -117,7 +118,7 @@ static void prof_collect(XrEnv *env) {
         float ms = 0.f;
         cudaEventSynchronize(p.b);
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { env->prof_ms[p.cls] += ms; env->prof_n[p.cls]++; }
-        if (p.step && p.grp >= 0 && p.grp < 2 && (p.cls == XR_K_ROUTE_WIN || p.cls == XR_K_OBS)) {
+        if (p.step && p.grp >= 0 && p.grp < XR_NG && (p.cls == XR_K_ROUTE_WIN || p.cls == XR_K_OBS)) {
             float o0 = 0.f, o1 = 0.f;
             if (cudaEventElapsedTime(&o0, p.step, p.a) == cudaSuccess && cudaEventElapsedTime(&o1, p.step, p.b) == cudaSuccess) {
                 if (p.cls == XR_K_ROUTE_WIN) {
@@ -148,7 +149,7 @@ static void xr_free(XrEnv *env) {
     if (env->p_flags) cudaFreeHost(env->p_flags);
     if (env->p_ids) cudaFreeHost(env->p_ids);
     if (env->p_lists) cudaFreeHost(env->p_lists);
-    for (int k = 0; k < 2; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
+    for (int k = 0; k < XR_NG; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
     for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : env->ev_pool) cudaEventDestroy(e);
@@ -244,7 +245,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * 8); DA(d.dbg, 16);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * 4 * XR_NG); DA(d.dbg, 16);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -262,7 +263,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
-        cudaMallocHost(&env->p_lists, sizeof(int32_t) * 10 * N) != cudaSuccess) {
+        cudaMallocHost(&env->p_lists, sizeof(int32_t) * (2 + 4 * XR_NG) * N) != cudaSuccess) {
         xr_free(env);
         return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
     }
@@ -272,7 +273,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_done.assign(N, 0); env->h_loaded.assign(N, 0); env->h_reset.assign(N, 0);
     env->h_nrem.assign(N, 0);
     env->h_netwin.assign(N * (g.max_nets + 1) * 2, 0);
-    env->win_margin = cfg->window_margin == 0 ? 10 : cfg->window_margin;
+    env->win_margin = cfg->window_margin == 0 ? 14 : cfg->window_margin;
     // 0 = auto: per step, as many CTAs per environment as keeps about two clusters per SM's worth
     env->min_cluster = cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2
                      : cfg->min_cluster == 1 ? 1 : 0;
@@ -282,13 +283,17 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     cudaFuncSetAttribute(k_route_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
-    for (int k = 0; k < 2; k++) {
-        cudaStreamCreateWithFlags(&env->gs[k], cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int k = 0; k < XR_NG; k++) {
+        // the heavier the group, the higher its stream priority: its clusters are placed first
+        cudaStreamCreateWithPriority(&env->gs[k], cudaStreamNonBlocking, k == 0 ? prio_lo : prio_hi);
         cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
     // tuning knobs (not part of the ABI): XR_HEAVY_PINS, XR_HEAVY_CLUSTER
-    if (const char *e = getenv("XR_HEAVY_PINS")) env->heavy_pins = std::max(2, atoi(e));
+    if (const char *e = getenv("XR_MEDIUM_PINS")) env->grp_pins[1] = std::max(2, atoi(e));
+    if (const char *e = getenv("XR_HEAVY_PINS")) env->grp_pins[2] = std::max(env->grp_pins[1], atoi(e));
     if (const char *e = getenv("XR_HEAVY_CLUSTER")) env->heavy_cluster = atoi(e);
     // dynamic shared memory of the x+z sweep
     const int smem = g.Z * g.Xp * 5;
@@ -565,7 +570,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         env->cur_step_ev = e; env->step_evs.push_back(e);
     }
     static const int CS[4] = {1, 2, 4, 8};
-    int nb[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    int nb[XR_NG][4] = {};
     int min_cluster = env->min_cluster;
     if (min_cluster == 0) {
         int n_route = 0;
@@ -575,8 +580,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         while (min_cluster < 8 && n_route * min_cluster * 2 <= 2 * env->n_sm) min_cluster <<= 1;
     }
     bool any_global = false;
-    int n_grp[2] = {0, 0};
-    int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then 8 lists of N: [group][bucket]
+    int n_grp[XR_NG] = {};
+    int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then 4*XR_NG lists of N: [group][bucket]
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
         int route = 0, mode = 0, grp = 0;
@@ -586,7 +591,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             const int WX = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2];
             const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
             int bucket = -1;
-            const int mc = (np >= env->heavy_pins && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
+            const int mc = (np >= env->grp_pins[XR_NG - 1] && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
             if (WX > 0) {
                 for (int b = 0; b < 4 && bucket < 0; b++) {
                     if (CS[b] < mc) continue;
@@ -595,7 +600,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
                     if (bytes <= env->smem_cap) bucket = b;
                 }
             }
-            grp = (np >= env->heavy_pins || bucket < 0) ? 1 : 0;
+            for (int k = 1; k < XR_NG; k++) if (np >= env->grp_pins[k]) grp = k;
+            if (bucket < 0) grp = XR_NG - 1;
             if (bucket >= 0) {
                 mode = 1;
                 env->p_lists[(size_t)(2 + grp * 4 + bucket) * g.N + nb[grp][bucket]++] = i;
@@ -610,7 +616,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     CK(cudaMemcpyAsync(env->d.mode, modes, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(env->d.grp, grps, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     if (any_route) {
-        CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * 8 * g.N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * 4 * XR_NG * g.N, cudaMemcpyHostToDevice, st));
         Launch L(env, XR_K_ROUTE_BEGIN, st);
         k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d);
     }
@@ -618,17 +624,20 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     CK(cudaGetLastError());
     // ---- the two post-route groups run on their own streams: the light group's metric and
     // observation kernels (HBM bound) overlap the heavy group's on-chip routing
-    int maxn_grp[2] = {0, 0};
+    int maxn_grp[XR_NG] = {};
     for (int i = 0; i < g.N; i++) {
         if (actions[i] == 0) continue;
         const int after = env->h_nrem[i] - (actions[i] >= 1 ? 1 : 0);
         maxn_grp[grps[i]] = std::max(maxn_grp[grps[i]], std::min(after, g.obs_max_nets));
     }
-    const bool split = n_grp[0] > 0 && n_grp[1] > 0 && any_route;
+    int n_nonempty = 0;
+    for (int k = 0; k < XR_NG; k++) n_nonempty += n_grp[k] > 0;
+    const bool split = n_nonempty > 1 && any_route;
     if (split) CK(cudaEventRecord(env->ev_fork, st));
-    for (int grp = 0; grp < 2; grp++) {
+    for (int gi = 0; gi < XR_NG; gi++) {
+        const int grp = XR_NG - 1 - gi;                   // heaviest group first: it is the long pole
         const bool has = n_grp[grp] > 0;
-        if (!has && grp == 1) continue;                   // (group 0 always runs: it also finalises idle envs)
+        if (!has && grp != 0) continue;                   // (group 0 always runs: it also finalises idle envs)
         cudaStream_t sg = split ? env->gs[grp] : st;
         env->cur_grp = grp;
         if (split) CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
@@ -682,7 +691,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -1); }
         { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -1); }
         {
-            int maxn = std::max(maxn_grp[0], maxn_grp[1]);
+            int maxn = 0;
+            for (int k = 0; k < XR_NG; k++) maxn = std::max(maxn, maxn_grp[k]);
             const long long total = (2ll + 7ll * maxn) * g.cells;
             Launch L(env, XR_K_OBS, st);
             k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, st>>>(env->g, env->d, 1);
@@ -931,7 +941,7 @@ extern "C" int xr_debug_timeline(XrEnv *env, double *out) {
     cudaSetDevice(env->device);
     cudaDeviceSynchronize();
     prof_collect(env);
-    for (int gidx = 0; gidx < 2; gidx++)
+    for (int gidx = 0; gidx < XR_NG; gidx++)
         for (int k = 0; k < 3; k++) {
             out[3 * gidx + k] = env->tl_n[gidx][k] ? env->tl_sum[gidx][k] / env->tl_n[gidx][k] : 0.0;
             env->tl_sum[gidx][k] = 0; env->tl_n[gidx][k] = 0;

@@ -237,9 +237,9 @@ class VecGame:
         return {k: int(out[i]) for i, k in enumerate(names) if k}
 
     def debug_timeline(self) -> dict:
-        out = (C.c_double * 6)()
+        out = (C.c_double * 9)()
         _lib.check(self._L.xr_debug_timeline(self._h, out), self._h)
-        return {f"g{g}_{n}": round(out[3 * g + k], 3) for g in range(2)
+        return {f"g{g}_{n}": round(out[3 * g + k], 3) for g in range(3)
                 for k, n in enumerate(("route_start", "route_end", "obs_end"))}
 
     def profile(self, enable: bool):
