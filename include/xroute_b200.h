@@ -178,6 +178,11 @@ int xr_debug_timeline(XrEnv *env, double *out);
 int xr_profile_enable(XrEnv *env, int32_t enable);
 int xr_profile_get(XrEnv *env, double *ms /*[XR_K_COUNT]*/, int64_t *launches /*[XR_K_COUNT]*/);
 
+/* Stand-alone timing of one HBM-bound kernel (XR_K_OBS or XR_K_METRICS) over all
+ * environments, for roofline accounting: mean ms of `reps` launches (CUDA events on
+ * `stream`) and the algorithmic bytes of one launch.  State is left unchanged.        */
+int xr_kernel_bench(XrEnv *env, int32_t which, int32_t reps, double *ms_out, double *bytes_out, void *stream);
+
 /* Stand-alone observation build from a decoded node stream (the eval-server path):
  * nodes int32 [n_nodes][6] = (x, y, z, used, Net, Pin) as produced by
  * handle_messange (baseline/baseline_utils.py:23-40); keep_nets uint8 [max_net+1]

@@ -56,7 +56,7 @@ SYMBOLS = [
     "xr_step", "xr_step_results", "xr_obs_layout", "xr_obs_channels", "xr_obs_copy",
     "xr_obs_dlpack", "xr_buffer_dlpack", "xr_buffer_ptr", "xr_legal_mask", "xr_get_paths",
     "xr_get_state", "xr_get_dist", "xr_stats_update", "xr_counters", "xr_profile_enable",
-    "xr_profile_get", "xr_build_obs_from_nodes", "xr_route_counters", "xr_debug_counters", "xr_debug_timeline",
+    "xr_profile_get", "xr_build_obs_from_nodes", "xr_route_counters", "xr_debug_counters", "xr_debug_timeline", "xr_kernel_bench",
 ]
 
 _lib = None
@@ -115,6 +115,8 @@ def load():
     L.xr_counters.argtypes = [vp, i64p, i64p, i64p, i64p]
     L.xr_route_counters.restype = C.c_int
     L.xr_route_counters.argtypes = [vp, i64p, i64p, i64p]
+    L.xr_kernel_bench.restype = C.c_int
+    L.xr_kernel_bench.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     L.xr_debug_timeline.restype = C.c_int
     L.xr_debug_timeline.argtypes = [vp, C.POINTER(C.c_double)]
     L.xr_debug_counters.restype = C.c_int

@@ -933,6 +933,57 @@ extern "C" int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *glob
     return XR_OK;
 }
 
+/* Stand-alone timing of one HBM-bound kernel over ALL environments of the handle (for the
+ * roofline: inside a step these kernels overlap the routing of other groups).  which:
+ * XR_K_OBS (rebuilds every observation in place, state unchanged) or XR_K_METRICS
+ * (congestion reduction; the partial sums are discarded).  Returns the mean milliseconds of
+ * `reps` launches after one warm-up, measured with CUDA events on `stream`, and the
+ * algorithmic bytes one launch moves.                                                  */
+extern "C" int xr_kernel_bench(XrEnv *env, int32_t which, int32_t reps, double *ms_out, double *bytes_out, void *stream) {
+    if (!env || reps < 1 || !ms_out) return XR_E_INVALID;
+    const Geo &g = env->g;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaSetDevice(env->device);
+    for (int i = 0; i < g.N; i++) if (!env->h_reset[i]) return fail(env, XR_E_STATE, "kernel bench before reset");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double bytes = 0;
+    if (which == XR_K_OBS) {
+        int maxn = 0;
+        for (int i = 0; i < g.N; i++) {
+            const int n = std::min(env->h_nrem[i], g.obs_max_nets);
+            maxn = std::max(maxn, n);
+            bytes += 4.0 * (2 + 7 * n) * g.cells;
+        }
+        const long long total = (2ll + 7ll * maxn) * g.cells;
+        dim3 grid((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N);
+        k_mark<<<(g.N + 255) / 256, 256, 0, st>>>(env->g, env->d, 1);
+        for (int r = 0; r <= reps; r++) {
+            if (r == 1) cudaEventRecord(a, st);
+            k_obs<<<grid, OBS_THREADS, 0, st>>>(env->g, env->d, 0);
+        }
+        cudaEventRecord(b, st);
+        env->n_launch += reps + 2;
+    } else if (which == XR_K_METRICS) {
+        bytes = 4.0 * g.cells * g.N;
+        for (int r = 0; r <= reps; r++) {
+            if (r == 1) cudaEventRecord(a, st);
+            k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -2);
+        }
+        cudaEventRecord(b, st);
+        cudaMemsetAsync(env->d.msum, 0, sizeof(unsigned) * 4 * g.N, st);
+        env->n_launch += reps + 1;
+    } else { cudaEventDestroy(a); cudaEventDestroy(b); return fail(env, XR_E_INVALID, "kernel bench: unknown kernel"); }
+    cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (e != cudaSuccess) { env->err = cudaGetErrorString(e); return XR_E_CUDA; }
+    *ms_out = ms / reps;
+    if (bytes_out) *bytes_out = bytes;
+    return XR_OK;
+}
+
 /* Profiling timeline (needs xr_profile_enable): mean offsets in ms from the start of a step
  * of, per post-route group g: out[3g+0] first route launch start, [3g+1] route end,
  * [3g+2] observation end.  Cleared on read.                                          */

@@ -97,23 +97,35 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d, int tag) {
 // per cell (cellinfo); apnet only for occupied AP cells.
 __global__ void __launch_bounds__(256) k_metrics(Geo g, Dev d, int pass) {
     const int env = blockIdx.y;
-    if (d.act[2 * env] < 1 || !pass_selects(d, env, pass)) return;
+    if (pass != -2 && (d.act[2 * env] < 1 || !pass_selects(d, env, pass))) return;   // -2: every env (kernel bench)
     const size_t eoff = (size_t)env * g.cells_p;
     const uint4 *ci4 = reinterpret_cast<const uint4 *>(d.cellinfo + eoff);
     const int n4 = g.cells_p >> 2;
     unsigned blocked = 0, shorted = 0, overflow = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(ci4 + i);
-        const uint32_t c[4] = {v.x, v.y, v.z, v.w};
+    // four independent 16-byte loads in flight per thread and trip
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+        uint4 v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t u = (c[k] & CI_USAGE_MASK) >> CI_USAGE_SHIFT;
-            if (u) {
-                blocked += (c[k] & CI_BLOCK) ? 1u : 0u;
-                bool sh = u >= 2u;
-                if (!sh && (c[k] & CI_ISAP)) sh = d.apnet[eoff + 4 * (size_t)i + k] != (c[k] & CI_OWNER_MASK);
-                shorted += sh ? 1u : 0u;
-                overflow += u - 1u;
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * stride;
+            v[u] = i < n4 ? __ldg(ci4 + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t c[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            if (((c[0] | c[1] | c[2] | c[3]) & CI_USAGE_MASK) == 0u) continue;    // nothing routed here
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t us = (c[k] & CI_USAGE_MASK) >> CI_USAGE_SHIFT;
+                if (us) {
+                    blocked += (c[k] & CI_BLOCK) ? 1u : 0u;
+                    bool sh = us >= 2u;
+                    if (!sh && (c[k] & CI_ISAP))
+                        sh = d.apnet[eoff + 4 * (size_t)(i0 + u * stride) + k] != (c[k] & CI_OWNER_MASK);
+                    shorted += sh ? 1u : 0u;
+                    overflow += us - 1u;
+                }
             }
         }
     }
@@ -128,9 +140,9 @@ __global__ void __launch_bounds__(256) k_metrics(Geo g, Dev d, int pass) {
     if (lane == 0) { sm[0][w] = blocked; sm[1][w] = shorted; sm[2][w] = overflow; }
     __syncthreads();
     if (threadIdx.x < 3) {
-        unsigned s = 0;
-        for (int k = 0; k < 8; k++) s += sm[threadIdx.x][k];
-        if (s) atomicAdd(&d.msum[4 * env + threadIdx.x], s);
+        unsigned sum = 0;
+        for (int k = 0; k < 8; k++) sum += sm[threadIdx.x][k];
+        if (sum) atomicAdd(&d.msum[4 * env + threadIdx.x], sum);
     }
 }
 

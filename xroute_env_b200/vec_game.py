@@ -236,6 +236,13 @@ class VecGame:
                  "", "", "ph_compact_y", "ph_sweep_y", "ph_compact_x", "ph_sweep_x", "ph_sweep_z", "lines_y", "lines_x"]
         return {k: int(out[i]) for i, k in enumerate(names) if k}
 
+    def kernel_bench(self, which: str, reps: int = 10) -> dict:
+        """Isolated timing of 'obs' or 'metrics' over all environments (roofline accounting)."""
+        ms, nbytes = C.c_double(), C.c_double()
+        _lib.check(self._L.xr_kernel_bench(self._h, _lib.K_NAMES.index(which), reps, C.byref(ms), C.byref(nbytes),
+                                           self._stream()), self._h)
+        return {"ms": ms.value, "bytes": nbytes.value, "gbs": nbytes.value / (ms.value * 1e-3) / 1e9 if ms.value else 0.0}
+
     def debug_timeline(self) -> dict:
         out = (C.c_double * 9)()
         _lib.check(self._L.xr_debug_timeline(self._h, out), self._h)
