@@ -76,7 +76,12 @@ typedef struct XrConfig {
                                   search; 0 = default (14), <0 = always use the full-grid sweeps  */
     int32_t min_cluster;       /* smallest CTA cluster per environment for the window kernel
                                   (1, 2, 4 or 8); 0 = auto (from the number of routing environments) */
-    int32_t reserved[5];
+    int32_t obs_mode;          /* 0 = observations are updated in place each step (only the cells that
+                                  change: new obstacle cells, the order channel, the access points of
+                                  the net blocks that shift down) -- bit-identical to a rebuild, the
+                                  consumer must treat the buffer as read-only;
+                                  1 = full rebuild of every stepped environment's observation        */
+    int32_t reserved[4];
 } XrConfig;
 
 /* cumulative metric slots of xr_step_results / XR_BUF_CUM */

@@ -71,6 +71,41 @@ def test_route_paths_agree_across_engines(kw):
     _run_episode(geom, insts, seed=8, **kw)
 
 
+@pytest.mark.parametrize("obs_mode", [0, 1], ids=["incremental", "full-rebuild"])
+def test_observation_modes_match_oracle(obs_mode):
+    """In-place incremental observation update (default) and the full per-step rebuild both
+    reproduce the reference layout bit-exactly at every step, across resets and capped nets."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    geom = ispd18_geometry(30, 28, 9)
+    insts = make_batch(geom, 4, 9, seed=930)
+    _run_episode(geom, insts, seed=10, obs_mode=obs_mode)
+    # second episode on the same handle, interrupted by a partial reset
+    vg = VecGame(geom, insts, device=0, obs_mode=obs_mode)
+    oracles = [OracleEnv(geom, i) for i in insts]
+    for rep in range(2):
+        vg.reset()
+        for o in oracles:
+            o.reset()
+        for t, net in enumerate((5, 2, 9, 1)):
+            vg.step(np.array([net] * 4, np.int32))
+            for e, o in enumerate(oracles):
+                o.step(net)
+                assert np.array_equal(vg.obs_host(e).numpy(), o.obs()), (rep, t, e)
+        vg.reset([0, 2])
+        oracles[0].reset(); oracles[2].reset()
+        vg.step(np.array([3, 3, 3, 3], np.int32))
+        for e, o in enumerate(oracles):
+            o.step(3)
+            assert np.array_equal(vg.obs_host(e).numpy(), o.obs()), (rep, "after partial reset", e)
+    # a new instance in slot 1 invalidates its buffer: the next reset rebuilds it
+    other = make_instance(geom, 5, 931)
+    vg.load_instance(1, other)
+    vg.reset([1])
+    assert np.array_equal(vg.obs_host(1).numpy(), OracleEnv(geom, other).obs())
+    vg.close()
+
+
 def test_window_fallback_counter_and_exactness():
     from xroute_env_b200 import VecGame
     geom = ispd18_geometry(64, 64, 9)

@@ -36,7 +36,7 @@ class XrConfig(C.Structure):
         ("via_cost", C.c_int32), ("grid_cost", C.c_int32), ("drc_cost", C.c_int32),
         ("fixed_shape_cost", C.c_int32), ("block_cost", C.c_int32),
         ("pumps_per_sync", C.c_int32), ("window_margin", C.c_int32), ("min_cluster", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("obs_mode", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 

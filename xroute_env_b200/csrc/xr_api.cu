@@ -41,6 +41,9 @@ struct XrEnv {
     int32_t *p_act = nullptr;           // pinned [N][2]
     int32_t *p_flags = nullptr;         // pinned [2]
     int32_t *p_ids = nullptr;           // pinned [N]
+    uint8_t *p_full = nullptr;          // pinned [N] reset: full observation build needed
+    std::vector<uint8_t> h_clean;       // observation buffer of the env satisfies the incremental invariant
+    int obs_mode = 0;
     int32_t *d_ids = nullptr;
     int pumps_per_sync = 4;
     // window-resident route kernel
@@ -148,6 +151,7 @@ static void xr_free(XrEnv *env) {
     if (env->p_act) cudaFreeHost(env->p_act);
     if (env->p_flags) cudaFreeHost(env->p_flags);
     if (env->p_ids) cudaFreeHost(env->p_ids);
+    if (env->p_full) cudaFreeHost(env->p_full);
     if (env->p_lists) cudaFreeHost(env->p_lists);
     for (int k = 0; k < XR_NG; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
@@ -241,7 +245,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.act, N * 2); DA(d.phase, N); DA(d.changed, N); DA(d.reinit, N); DA(d.first, N);
     DA(d.ap_conn, N * g.max_aps); DA(d.flags, 4);
     DA(d.msum, N * 4); DA(d.delta, N * 3); DA(d.cum, N * 6); DA(d.wlvia, N * 2); DA(d.done, N);
-    DA(d.reward, N); DA(d.envstat, N * 8); DA(d.stats, XR_STATS_COUNT); DA(d.obs_do, N);
+    DA(d.reward, N); DA(d.envstat, N * 8); DA(d.stats, XR_STATS_COUNT); DA(d.obs_do, N); DA(d.obs_full, N);
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
@@ -263,6 +267,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
+        cudaMallocHost(&env->p_full, N) != cudaSuccess ||
         cudaMallocHost(&env->p_lists, sizeof(int32_t) * (2 + 4 * XR_NG) * N) != cudaSuccess) {
         xr_free(env);
         return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
@@ -272,6 +277,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_npins.assign(N * (g.max_nets + 1), 0);
     env->h_done.assign(N, 0); env->h_loaded.assign(N, 0); env->h_reset.assign(N, 0);
     env->h_nrem.assign(N, 0);
+    env->h_clean.assign(N, 0);
+    env->obs_mode = cfg->obs_mode == 1 ? 1 : 0;
     env->h_netwin.assign(N * (g.max_nets + 1) * 2, 0);
     env->win_margin = cfg->window_margin == 0 ? 14 : cfg->window_margin;
     // 0 = auto: per step, as many CTAs per environment as keeps about two clusters per SM's worth
@@ -421,6 +428,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
     CK(cudaMemcpy(d.net_win + e * (g.max_nets + 1) * 6, netwin.data(), sizeof(int32_t) * (g.max_nets + 1) * 6, cudaMemcpyHostToDevice));
     env->h_loaded[env_id] = 1;
     env->h_reset[env_id] = 0;
+    env->h_clean[env_id] = 0;            // the access points changed: the next reset rebuilds the observation
     return XR_OK;
 }
 
@@ -475,8 +483,20 @@ extern "C" int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *str
             k_mark_ids<<<((int)ids.size() + 255) / 256, 256, 0, st>>>(env->g, env->d, env->d_ids, (int)ids.size());
         }
     }
+    // which environments need a full observation build (first reset, new instance, obs_mode 1)
+    CK(cudaStreamSynchronize(st)); env->n_sync++;          // p_full is reused across calls
+    bool any_full = false, any_inc = false;
+    memset(env->p_full, 0, g.N);
+    for (int id : ids) {
+        const bool full = env->obs_mode == 1 || !env->h_clean[id];
+        env->p_full[id] = full;
+        any_full |= full; any_inc |= !full;
+    }
+    CK(cudaMemcpyAsync(env->d.obs_full, env->p_full, g.N, cudaMemcpyHostToDevice, st));
+    if (any_inc) { Launch L(env, XR_K_OBS, st); k_obs_reset_clear<<<g.N, 256, 0, st>>>(env->g, env->d); }
     { Launch L(env, XR_K_MISC, st); k_reset_cells<<<dim3(grid_cells(g, 1), g.N), 256, 0, st>>>(env->g, env->d); }
     { Launch L(env, XR_K_MISC, st); k_reset_env<<<nb, 256, 0, st>>>(env->g, env->d); }
+    if (any_inc) { Launch L(env, XR_K_OBS, st); k_obs_reset_set<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d); }
     CK(cudaGetLastError());
     for (int id : ids) {
         uint8_t *routed = &env->h_routed[(size_t)id * (g.max_nets + 1)];
@@ -487,7 +507,9 @@ extern "C" int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *str
         env->h_nrem[id] = n;
         env->h_done[id] = (n == 0);
         env->h_reset[id] = 1;
+        env->h_clean[id] = 1;
     }
+    if (!any_full) return XR_OK;
     return launch_obs(env, st);
 }
 
@@ -649,9 +671,11 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
         { Launch L(env, XR_K_MISC, sg); k_finalize<<<(g.N + 127) / 128, 128, 0, sg>>>(env->g, env->d, grp); }
         if (has) {
-            const long long total = (2ll + 7ll * maxn_grp[grp]) * g.cells;
             Launch L(env, XR_K_OBS, sg);
-            k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, sg>>>(env->g, env->d, grp + 2);
+            if (env->obs_mode == 1) {
+                const long long total = (2ll + 7ll * maxn_grp[grp]) * g.cells;
+                k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, sg>>>(env->g, env->d, grp + 2);
+            } else k_obs_update<<<g.N, 256, 0, sg>>>(env->g, env->d, grp + 2);
         }
         if (split) { CK(cudaEventRecord(env->ev_join[grp], sg)); CK(cudaStreamWaitEvent(st, env->ev_join[grp], 0)); }
     }
@@ -695,7 +719,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             for (int k = 0; k < XR_NG; k++) maxn = std::max(maxn, maxn_grp[k]);
             const long long total = (2ll + 7ll * maxn) * g.cells;
             Launch L(env, XR_K_OBS, st);
-            k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, st>>>(env->g, env->d, 1);
+            if (env->obs_mode == 1)
+                k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, st>>>(env->g, env->d, 1);
+            else k_obs_update<<<g.N, 256, 0, st>>>(env->g, env->d, 1);
         }
         CK(cudaGetLastError());
     }
@@ -960,7 +986,7 @@ extern "C" int xr_kernel_bench(XrEnv *env, int32_t which, int32_t reps, double *
         k_mark<<<(g.N + 255) / 256, 256, 0, st>>>(env->g, env->d, 1);
         for (int r = 0; r <= reps; r++) {
             if (r == 1) cudaEventRecord(a, st);
-            k_obs<<<grid, OBS_THREADS, 0, st>>>(env->g, env->d, 0);
+            k_obs<<<grid, OBS_THREADS, 0, st>>>(env->g, env->d, -1);
         }
         cudaEventRecord(b, st);
         env->n_launch += reps + 2;
@@ -1117,7 +1143,7 @@ extern "C" int xr_build_obs_from_nodes(int32_t device, int32_t X, int32_t Y, int
     cudaMemcpyAsync(d.net_start, ns2.data(), sizeof(int32_t) * (g.max_nets + 2), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d.ap_obsoff, obsoff.data(), sizeof(int32_t) * g.max_aps, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d.ap_adj, adj.data(), g.max_aps, cudaMemcpyHostToDevice, st);
-    k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), 1), OBS_THREADS, 0, st>>>(g, d, 0);
+    k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), 1), OBS_THREADS, 0, st>>>(g, d, -1);
     cudaMemcpyAsync(host_out, d.obs, sizeof(float) * total, cudaMemcpyDeviceToHost, st);
     ce = cudaStreamSynchronize(st);
     freeall();

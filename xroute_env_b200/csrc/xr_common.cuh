@@ -85,6 +85,7 @@ struct Dev {
     long long *stats;     // [16]
     unsigned long long *dbg; // [8] window-kernel diagnostics: iterations, connections, relax cycles, kernel cycles, nets, window cells
     uint8_t  *obs_do;     // [N]
+    uint8_t  *obs_full;   // [N] reset: 1 = full observation build, 0 = incremental (buffer invariant holds)
     float    *obs;        // [N][obs_stride]
     // last routed paths (parity / debug)
     int32_t  *path;       // [N][path_cap] canonical indices

@@ -30,7 +30,7 @@ __device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
 
 __global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d, int tag) {
     const int env = blockIdx.y;
-    if (!d.obs_do[env] || (tag != 0 && d.fin[env] != tag)) return;
+    if (!d.obs_do[env] || (tag > 0 && d.fin[env] != tag) || (tag == 0 && !d.obs_full[env])) return;   // tag -1: all flagged
     const int n_rem = d.n_remaining[env];
     const int n = n_rem < g.obs_max_nets ? n_rem : g.obs_max_nets;
     const long long cells = g.cells;
@@ -86,6 +86,81 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(Geo g, Dev d, int tag) {
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------- incremental observation
+// The observation buffer persists between steps and, outside channels 0 and 1, is zero
+// everywhere except at the access points of the remaining nets (invariant, established by
+// the first full build).  Routing net a removes its 7-channel block and shifts every later
+// block down by one (channel compaction) -- which only moves the few
+// access-point ones: clear them at the old block, set them at the new one.  Channel 0 is
+// patched by commit_cell, channel 1 is rewritten here.  One CTA per environment.
+__device__ __forceinline__ void obs_mark_net(const Geo &g, const Dev &d, int env, int net, int block, float val) {
+    if (block >= g.obs_max_nets) return;
+    const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
+    const size_t aoff = (size_t)env * g.max_aps;
+    float *out = d.obs + (size_t)env * g.obs_stride + (2ll + 7ll * block) * g.cells;
+    for (int i = ns[net] + threadIdx.x; i < ns[net + 1]; i += blockDim.x) {
+        const int off = d.ap_obsoff[aoff + i];
+        out[off] = val;
+        if (d.ap_adj[aoff + i]) {
+#pragma unroll
+            for (int j = 1; j <= 6; j++) out[(size_t)j * g.cells + off] = val;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_obs_update(Geo g, Dev d, int tag) {
+    const int env = blockIdx.x;
+    if (!d.obs_do[env] || d.fin[env] != tag) return;
+    const int a = d.act[2 * env];
+    if (a < 1) return;                                     // idle / stop: nothing moves
+    const int n = d.n_remaining[env];                      // after the step
+    const int *rank = d.rank_net + (size_t)env * g.max_nets;
+    int ra = 0;                                            // old rank of a = remaining nets with a smaller id
+    while (ra < n && rank[ra] < a) ra++;
+    // clear: the routed net at its old block, every later net at its old block (new rank + 1)
+    obs_mark_net(g, d, env, a, ra, 0.f);
+    for (int k = ra; k < n; k++) obs_mark_net(g, d, env, rank[k], k + 1, 0.f);
+    __syncthreads();
+    // set: every later net at its new block
+    for (int k = ra; k < n; k++) obs_mark_net(g, d, env, rank[k], k, 1.f);
+    // order channel: n ids then a zero where the old last id was
+    float *ch1 = d.obs + (size_t)env * g.obs_stride + g.cells;
+    for (int k = ra + threadIdx.x; k <= n; k += blockDim.x) if (k < g.cells) ch1[k] = k < n ? (float)rank[k] : 0.f;
+}
+
+// Incremental reset, part 1 (before k_reset_env recomputes the rank list): remove the
+// access-point ones and order ids of the nets that are still in the observation.
+__global__ void __launch_bounds__(256) k_obs_reset_clear(Geo g, Dev d) {
+    const int env = blockIdx.x;
+    if (!d.obs_do[env] || d.obs_full[env]) return;
+    const int n = d.n_remaining[env];
+    const int *rank = d.rank_net + (size_t)env * g.max_nets;
+    for (int k = 0; k < n; k++) obs_mark_net(g, d, env, rank[k], k, 0.f);
+    float *ch1 = d.obs + (size_t)env * g.obs_stride + g.cells;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) if (k < g.cells) ch1[k] = 0.f;
+}
+// part 2 (after k_reset_cells / k_reset_env): channel 0 from the blockage bytes, every net
+// at its initial rank, the order channel.  grid (chunks, N).
+__global__ void __launch_bounds__(256) k_obs_reset_set(Geo g, Dev d) {
+    const int env = blockIdx.y;
+    if (!d.obs_do[env] || d.obs_full[env]) return;
+    float *out = d.obs + (size_t)env * g.obs_stride;
+    const uint8_t *ob = d.obst_obs + (size_t)env * g.cells_o;
+    const int n4 = g.cells >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const uchar4 b = reinterpret_cast<const uchar4 *>(ob)[i];
+        reinterpret_cast<float4 *>(out)[i] = make_float4(b.x ? 1.f : 0.f, b.y ? 1.f : 0.f, b.z ? 1.f : 0.f, b.w ? 1.f : 0.f);
+    }
+    if (blockIdx.x == 0) {
+        for (int i = n4 * 4 + threadIdx.x; i < g.cells; i += blockDim.x) out[i] = ob[i] ? 1.f : 0.f;
+        const int n = d.n_remaining[env];
+        const int *rank = d.rank_net + (size_t)env * g.max_nets;
+        for (int k = 0; k < n; k++) obs_mark_net(g, d, env, rank[k], k, 1.f);
+        float *ch1 = out + g.cells;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) if (k < g.cells) ch1[k] = (float)rank[k];
     }
 }
 

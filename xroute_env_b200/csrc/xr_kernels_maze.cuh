@@ -337,7 +337,9 @@ __device__ __forceinline__ void commit_cell(const Geo &g, const Dev &d, int env,
     if (((ci & CI_USAGE_MASK) >> CI_USAGE_SHIFT) < 255u) ci += 1u << CI_USAGE_SHIFT;
     if ((ci & CI_OWNER_MASK) == 0u) ci |= (uint32_t)net;
     d.cellinfo[c] = ci;
-    d.obst_obs[(size_t)env * g.cells_o + ((size_t)x * g.Y + y) * g.Z + z] = 1;
+    const size_t oo = ((size_t)x * g.Y + y) * g.Z + z;
+    d.obst_obs[(size_t)env * g.cells_o + oo] = 1;
+    d.obs[(size_t)env * g.obs_stride + oo] = 1.f;        // channel 0 of the observation, updated in place
     d.cflag[c] |= CF_TREE;
     d.dist[c] = 0;
 }

@@ -659,6 +659,8 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         atomicAdd(&d.dbg[0], (unsigned long long)n_iter); atomicAdd(&d.dbg[1], (unsigned long long)n_conn);
         atomicAdd(&d.dbg[2], (unsigned long long)cyc_relax); atomicAdd(&d.dbg[3], (unsigned long long)(clock64() - tk0));
         atomicAdd(&d.dbg[4], 1ull); atomicAdd(&d.dbg[5], (unsigned long long)(WX * WY));
+        if (C == 8) { atomicAdd(&d.dbg[6], (unsigned long long)n_iter); atomicAdd(&d.dbg[7], (unsigned long long)cyc_relax);
+                      atomicAdd(&d.dbg[15], (unsigned long long)n_conn); }
 #ifdef WIN_PHASE_TIMING
         for (int k = 0; k < 7; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)ph[k]);
 #endif

@@ -26,7 +26,7 @@ class VecGame:
     def __init__(self, geom: Geometry, instances: list[Instance], *, device: int = 0,
                  max_nets: int | None = None, max_aps: int | None = None,
                  obs_max_nets: int = -1, path_capacity: int = 0, pumps_per_sync: int = 0,
-                 window_margin: int = 0, min_cluster: int = 0):
+                 window_margin: int = 0, min_cluster: int = 0, obs_mode: int = 0):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.geom = geom
@@ -53,6 +53,7 @@ class VecGame:
         cfg.fixed_shape_cost, cfg.block_cost = geom.fixed_shape_cost, geom.block_cost
         cfg.pumps_per_sync = pumps_per_sync
         cfg.window_margin, cfg.min_cluster = window_margin, min_cluster
+        cfg.obs_mode = obs_mode
         rc = self._L.xr_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()
@@ -233,7 +234,8 @@ class VecGame:
         out = (C.c_uint64 * 16)()
         _lib.check(self._L.xr_debug_counters(self._h, out), self._h)
         names = ["win_iterations", "win_connections", "win_relax_cycles", "win_kernel_cycles", "win_nets", "win_area",
-                 "", "", "ph_compact_y", "ph_sweep_y", "ph_compact_x", "ph_sweep_x", "ph_sweep_z", "lines_y", "lines_x"]
+                 "c8_iterations", "c8_relax_cycles", "ph_compact_y", "ph_sweep_y", "ph_compact_x", "ph_sweep_x",
+                 "ph_sweep_z", "lines_y", "lines_x", "c8_connections"]
         return {k: int(out[i]) for i, k in enumerate(names) if k}
 
     def kernel_bench(self, which: str, reps: int = 10) -> dict:
