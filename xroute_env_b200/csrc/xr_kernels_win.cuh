@@ -114,6 +114,82 @@ __device__ __forceinline__ uint32_t win_walk(uint32_t *__restrict__ p, int n, in
     return ch;
 }
 
+// Group-cooperative exact relaxation of one line (both directions), for long lines when few
+// are dirty: G lanes (a power of two, G*q >= n) share the line, lane g owns the q consecutive
+// cells from g*q.  Each direction is a min-plus scan: every lane folds its cells into a
+// function pair (W, D): t -> min(t + W, D), the pairs are composed across the group with
+// log2(G) shuffle steps, and the carries are applied.  Serial depth 2q + log2(G) instead
+// of n.  q is odd so the lanes of a group hit distinct banks.  Returns the smallest
+// distance written (0xFFFFFFFF = none).
+#define WIN_QMAX 7
+__device__ __forceinline__ uint32_t win_scan_line(bool active, uint32_t *__restrict__ p, int n, int q, int G, int g,
+                                                  uint32_t lutreg, uint32_t pen, const uint32_t *__restrict__ len,
+                                                  const uint32_t *__restrict__ wl, bool uni,
+                                                  uint8_t *__restrict__ fa, uint8_t *__restrict__ fb) {
+    uint32_t dv[WIN_QMAX], wf[WIN_QMAX], wb[WIN_QMAX], fl[WIN_QMAX];
+    const int i0 = g * q;
+    unsigned chg = 0, valid = 0;
+#pragma unroll
+    for (int k = 0; k < WIN_QMAX; k++) {
+        const int i = i0 + k;
+        const bool ok = active && k < q && i < n;
+        valid |= ok ? (1u << k) : 0u;
+        const uint32_t v = ok ? p[i] : 0x0FFFFFFFu;
+        dv[k] = v & WMASK; fl[k] = v & ~WMASK;
+        if (uni) { const uint32_t w = ok ? wl[(v >> 28) & 7u] : 0u; wf[k] = w; wb[k] = w; }
+        else {
+            wf[k] = ok ? win_w(lutreg, pen, len[i], v) : 0u;
+            wb[k] = ok ? win_w(lutreg, pen, len[i + 1], v) : 0u;
+        }
+    }
+    {   // forward
+        uint32_t W = 0, D = WINF;
+#pragma unroll
+        for (int k = 0; k < WIN_QMAX; k++) { D = xr_min(D + wf[k], dv[k]); W = xr_min(W + wf[k], WINF); }
+        for (int off = 1; off < G; off <<= 1) {
+            const uint32_t Wo = __shfl_up_sync(0xFFFFFFFFu, W, off, G);
+            const uint32_t Do = __shfl_up_sync(0xFFFFFFFFu, D, off, G);
+            if (g >= off) { D = xr_min(Do + W, D); W = xr_min(Wo + W, WINF); }
+        }
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, D, 1, G);
+        if (g == 0) t = WINF;
+#pragma unroll
+        for (int k = 0; k < WIN_QMAX; k++) {
+            t = xr_min(t + wf[k], dv[k]);
+            if (t < dv[k]) { dv[k] = t; chg |= 1u << k; }
+        }
+    }
+    {   // backward
+        uint32_t W = 0, D = WINF;
+#pragma unroll
+        for (int k = WIN_QMAX - 1; k >= 0; k--) { D = xr_min(D + wb[k], dv[k]); W = xr_min(W + wb[k], WINF); }
+        for (int off = 1; off < G; off <<= 1) {
+            const uint32_t Wo = __shfl_down_sync(0xFFFFFFFFu, W, off, G);
+            const uint32_t Do = __shfl_down_sync(0xFFFFFFFFu, D, off, G);
+            if (g + off < G) { D = xr_min(Do + W, D); W = xr_min(Wo + W, WINF); }
+        }
+        uint32_t t = __shfl_down_sync(0xFFFFFFFFu, D, 1, G);
+        if (g == G - 1) t = WINF;
+#pragma unroll
+        for (int k = WIN_QMAX - 1; k >= 0; k--) {
+            t = xr_min(t + wb[k], dv[k]);
+            if (t < dv[k]) { dv[k] = t; chg |= 1u << k; }
+        }
+    }
+    chg &= valid;                        // padding cells (identity elements) are never written
+    uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < WIN_QMAX; k++) {
+        if ((chg >> k) & 1u) {
+            const int i = i0 + k;
+            p[i] = fl[k] | dv[k];
+            fa[i] = 1; fb[i] = 1;
+            mn = xr_min(mn, dv[k]);
+        }
+    }
+    return mn;
+}
+
 // one thread per dirty (z, x) column of the band: forward from the upper halo, back from the lower
 __device__ uint32_t win_sweep_y(const WinCtx &c, int n, long long &work) {
     uint32_t ch = 0xFFFFFFFFu;
@@ -140,8 +216,28 @@ __device__ uint32_t win_sweep_y(const WinCtx &c, int n, long long &work) {
 }
 
 // one thread per dirty (z, ly) row of the band
+#ifndef WIN_COOP_X_LINES
+#define WIN_COOP_X_LINES 512         // at most this many dirty rows ...
+#endif
+#ifndef WIN_COOP_X_LEN
+#define WIN_COOP_X_LEN 64            // ... of at least this many cells: lanes cooperate on each row
+#endif
 __device__ uint32_t win_sweep_x(const WinCtx &c, int n, long long &work) {
     uint32_t ch = 0xFFFFFFFFu;
+    if (n <= WIN_COOP_X_LINES && c.WX >= WIN_COOP_X_LEN && c.WX <= 32 * WIN_QMAX) {
+        const int G = 32, q = ((c.WX + G - 1) / G) | 1;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int k = warp; k < n; k += WIN_T / 32) {      // one warp per row (warp-uniform trip count)
+            const int row = c.list[k];
+            const int z = row / c.H, ly = row - z * c.H + 1;
+            uint32_t *p = c.cell + ((size_t)z * c.HH + ly) * c.WXp;
+            ch = xr_min(ch, win_scan_line(true, p, c.WX, q, G, lane, c.lutm[0 * c.Z + z], c.pens[z], c.lenx,
+                                          c.wlut + (0 * c.Z + z) * 8, c.uni_x != 0,
+                                          c.cold + z * c.WX, c.posd + (ly - 1) * c.WX));
+            if (lane == 0) work += c.WX;
+        }
+        return ch;
+    }
     for (int k = threadIdx.x; k < n; k += WIN_T) {
         const int row = c.list[k];
         const int z = row / c.H, ly = row - z * c.H + 1;
