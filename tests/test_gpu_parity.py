@@ -290,3 +290,13 @@ def test_game_dropin_episode_matches_oracle():
         assert (vio, wl, via) == (m["d_violation"], m["d_wirelength"], m["d_via"]) and done == bool(m["done"])
         assert np.array_equal(obs.numpy(), orc.obs()) and game.legal_action_set == set(orc.remaining())
     assert done and obs.shape[1] == 2 and game.routed_nets == {1, 2, 3, 4, 5}
+
+
+def test_ppo_rollout_example_runs():
+    """configs[4]: policy consumes the DLPack observation block; whole episodes complete."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "ppo_rollout.py"), "--envs", "64", "--nets", "6",
+                          "--steps", "14"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "env-steps/s" in out.stdout and "episodes finished 128" in out.stdout, out.stdout
