@@ -300,3 +300,17 @@ def test_ppo_rollout_example_runs():
                           "--steps", "14"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "env-steps/s" in out.stdout and "episodes finished 128" in out.stdout, out.stdout
+
+
+@pytest.mark.parametrize("name", ["t1_7x7_y79800", "t1_7x7_y319200", "t1_7x7_y79800_union", "t1_1x1_gx3_gy6",
+                                  "t1_1x1_gx2_gy6"])
+def test_real_ispd18_test1_regions(name):
+    """Row f1 / configs[0]: the regions extracted from the ispd18_test1 LEF/DEF/guide files
+    (tests/golden/ispd18_test1_regions.npz, tools/make_ispd_regions.py) -- two copies of the
+    region in one batch routed in different random orders, bit-exact against the oracle.
+    The *_union region lies on the union of all layers' tracks (non-uniform pitch)."""
+    import os
+    from xroute_env_b200.ispd import load_regions
+    g, inst = load_regions(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                        "ispd18_test1_regions.npz"))[name]
+    _run_episode(g, [inst, inst], seed=17, check_obs_every=5)

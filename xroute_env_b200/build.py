@@ -20,6 +20,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    cmd[1:1] = os.environ.get("XR_NVCC_EXTRA", "").split()      # e.g. -DWIN_PHASE_TIMING for tools/diag_route.py
     subprocess.check_call(cmd)
     return OUT
 

@@ -1,0 +1,458 @@
+"""LEF/DEF/guide -> region instances.
+
+Turns an ISPD-2018 style benchmark (``/root/reference/ispd/ispd18_test1/ispd18_test1.input.{lef,def,guide}``)
+into the region instances the environment routes: the track grid of a worker's route box,
+blockages from fixed Metal shapes, access points (APs) from the pin shapes of the nets that
+have to be connected inside the box, plus *boundary pins* where a net's global-route guide
+leaves the box.  This is the role of the simulator's region dump
+(``ispd/ispd18_test1/dump/workerx39900_y79800/worker.bin``: routeBox (39900,79800)-(79800,119700),
+extBox +-2000 DBU, i.e. 7x7 gcells of 5700 DBU; ``examples/launch_training.py:33-62`` picks such a
+directory per episode) -- the dump itself cannot be replayed (``design.odb`` is absent), so
+the regions are rebuilt from the design files.
+
+Stated simplifications against TritonRoute's pin access (the binary is absent, nothing
+to be bit-compatible with): APs are snapped to on-track crossings of the pin's layer
+(TritonRoute also adds off-track coordinates to the grid); a fixed shape blocks the
+crossings closer than ``width/2 + spacing`` to it.
+
+Pure host-side Python/numpy: it only produces the plain arrays of ``instances.Instance``;
+both the CUDA library and the CPU oracle consume those.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .instances import Geometry, Instance
+
+
+# ------------------------------------------------------------------ parsers
+@dataclass
+class LefLayer:
+    name: str
+    direction: int        # 0 = HORIZONTAL (preferred axis x)
+    pitch: int            # DBU
+    width: int
+    spacing: int
+
+
+@dataclass
+class LefMacro:
+    name: str
+    size: tuple[int, int]
+    pins: dict = field(default_factory=dict)     # pin -> {"use": str, "rects": [(layer, x0, y0, x1, y1)]}
+    obs: list = field(default_factory=list)      # [(layer, x0, y0, x1, y1)]
+
+
+@dataclass
+class Lef:
+    dbu: int
+    layers: list            # routing layers bottom-up
+    macros: dict
+
+    def layer_index(self, name: str) -> int:
+        for i, l in enumerate(self.layers):
+            if l.name == name:
+                return i
+        return -1
+
+
+def _tokens(path: str):
+    with open(path) as f:
+        for line in f:
+            line = line.split("#", 1)[0]
+            yield from line.split()
+
+
+def parse_lef(path: str) -> Lef:
+    """Routing layers (direction, pitch, width, spacing) and macros (size, pin ports, OBS)."""
+    tk = list(_tokens(path))
+    n = len(tk)
+    dbu = 1000
+    i = 0
+    while i < n:                                   # UNITS ... DATABASE MICRONS <dbu>
+        if tk[i] == "DATABASE" and i + 2 < n and tk[i + 1] == "MICRONS":
+            dbu = int(float(tk[i + 2]))
+            break
+        i += 1
+    to = lambda s: int(round(float(s) * dbu))
+    layers, macros = [], {}
+    i = 0
+    while i < n:
+        t = tk[i]
+        if t == "LAYER" and i + 2 < n and tk[i + 2] != ";":      # (inside VIA/PIN blocks it reads "LAYER name ;")
+            name = tk[i + 1]
+            j = i + 2
+            kind, direction, pitch, width, spacing = None, 0, 0, 0, 0
+            while j < n and not (tk[j] == "END" and tk[j + 1] == name):
+                if tk[j] == "TYPE":
+                    kind = tk[j + 1]
+                elif tk[j] == "DIRECTION":
+                    direction = 0 if tk[j + 1] == "HORIZONTAL" else 1
+                elif tk[j] == "PITCH":
+                    pitch = to(tk[j + 1])
+                elif tk[j] == "WIDTH" and width == 0 and tk[j - 1] != "PARALLELRUNLENGTH" and tk[j + 2] == ";":
+                    width = to(tk[j + 1])
+                elif tk[j] == "SPACING" and spacing == 0:
+                    spacing = to(tk[j + 1])
+                j += 1
+            if kind == "ROUTING":
+                layers.append(LefLayer(name, direction, pitch, width, spacing))
+            i = j + 2
+            continue
+        if t == "MACRO":
+            m = LefMacro(tk[i + 1], (0, 0))
+            j = i + 2
+            while j < n and not (tk[j] == "END" and tk[j + 1] == m.name):
+                if tk[j] == "SIZE":
+                    m.size = (to(tk[j + 1]), to(tk[j + 3]))
+                    j += 4
+                elif tk[j] == "PIN":
+                    pname = tk[j + 1]
+                    pin = {"use": "SIGNAL", "rects": []}
+                    j += 2
+                    layer = None
+                    while not (tk[j] == "END" and tk[j + 1] == pname):
+                        if tk[j] == "USE":
+                            pin["use"] = tk[j + 1]
+                        elif tk[j] == "LAYER":
+                            layer = tk[j + 1]
+                        elif tk[j] == "RECT":
+                            k = j + 1
+                            if tk[k] == "MASK":
+                                k += 2
+                            pin["rects"].append((layer, to(tk[k]), to(tk[k + 1]), to(tk[k + 2]), to(tk[k + 3])))
+                        j += 1
+                    m.pins[pname] = pin
+                    j += 2
+                elif tk[j] == "OBS":
+                    j += 1
+                    layer = None
+                    while tk[j] != "END":
+                        if tk[j] == "LAYER":
+                            layer = tk[j + 1]
+                        elif tk[j] == "RECT":
+                            k = j + 1
+                            if tk[k] == "MASK":
+                                k += 2
+                            m.obs.append((layer, to(tk[k]), to(tk[k + 1]), to(tk[k + 2]), to(tk[k + 3])))
+                        j += 1
+                    j += 1
+                else:
+                    j += 1
+            macros[m.name] = m
+            i = j + 2
+            continue
+        i += 1
+    return Lef(dbu, layers, macros)
+
+
+@dataclass
+class Def:
+    dbu: int
+    die: tuple[int, int, int, int]
+    tracks: dict            # layer -> {"X": [(start, n, step)], "Y": [...]}
+    components: dict        # name -> (macro, x, y, orient)
+    nets: dict              # name -> [(component, pin)]   (insertion order = file order)
+
+
+def parse_def(path: str) -> Def:
+    text = open(path).read()
+    dbu = int(re.search(r"UNITS\s+DISTANCE\s+MICRONS\s+(\d+)", text).group(1))
+    m = re.search(r"DIEAREA\s+\(\s*(-?\d+)\s+(-?\d+)\s*\)\s*\(\s*(-?\d+)\s+(-?\d+)\s*\)", text)
+    die = tuple(int(v) for v in m.groups())
+    tracks: dict = {}
+    for ax, start, cnt, step, layers in re.findall(r"TRACKS\s+([XY])\s+(-?\d+)\s+DO\s+(\d+)\s+STEP\s+(\d+)\s+LAYER\s+([^;]+);", text):
+        for layer in layers.split():
+            tracks.setdefault(layer, {"X": [], "Y": []})[ax].append((int(start), int(cnt), int(step)))
+    comps = {}
+    cm = re.search(r"\nCOMPONENTS\s+\d+\s*;(.*?)\nEND COMPONENTS", text, re.S)
+    if cm:
+        for name, macro, x, y, orient in re.findall(
+                r"-\s+(\S+)\s+(\S+)[^;]*?\+\s+(?:PLACED|FIXED|COVER)\s+\(\s*(-?\d+)\s+(-?\d+)\s*\)\s+(\w+)", cm.group(1)):
+            comps[name] = (macro, int(x), int(y), orient)
+    nets = {}
+    nm = re.search(r"\nNETS\s+\d+\s*;(.*?)\nEND NETS", text, re.S)
+    if nm:
+        for blk in nm.group(1).split(";"):
+            blk = blk.strip()
+            if not blk.startswith("-"):
+                continue
+            name = blk.split()[1]
+            nets[name] = [(c, p) for c, p in re.findall(r"\(\s*(\S+)\s+(\S+)\s*\)", blk) if c != "PIN"]
+    return Def(dbu, die, tracks, comps, nets)
+
+
+def parse_guide(path: str) -> dict:
+    """``net -> [(x0, y0, x1, y1, layer_name)]`` (ISPD-2018 guide format)."""
+    guides: dict = {}
+    cur = None
+    with open(path) as f:
+        for line in f:
+            s = line.split()
+            if not s:
+                continue
+            if len(s) == 1:
+                if s[0] == "(":
+                    continue
+                if s[0] == ")":
+                    cur = None
+                    continue
+                cur = guides.setdefault(s[0], [])
+            elif len(s) == 5 and cur is not None:
+                cur.append((int(s[0]), int(s[1]), int(s[2]), int(s[3]), s[4]))
+    return guides
+
+
+# ------------------------------------------------------------------ geometry helpers
+def _orient(rect, size, place, orient):
+    """Macro-local rect -> die coordinates for a DEF placement (lower-left ``place``)."""
+    x0, y0, x1, y1 = rect
+    w, h = size
+    px, py = place
+    def tr(x, y):
+        if orient == "N":  return px + x, py + y
+        if orient == "S":  return px + w - x, py + h - y
+        if orient == "FN": return px + w - x, py + y
+        if orient == "FS": return px + x, py + h - y
+        if orient == "W":  return px + h - y, py + x
+        if orient == "E":  return px + y, py + w - x
+        if orient == "FW": return px + y, py + x
+        if orient == "FE": return px + h - y, py + w - x
+        raise ValueError(f"unknown orientation {orient}")
+    ax, ay = tr(x0, y0)
+    bx, by = tr(x1, y1)
+    return min(ax, bx), min(ay, by), max(ax, bx), max(ay, by)
+
+
+def _track_coords(specs, lo, hi):
+    out = set()
+    for start, cnt, step in specs:
+        k0 = max(0, -(-(lo - start) // step))
+        k1 = min(cnt - 1, (hi - start) // step)
+        out.update(start + step * k for k in range(k0, k1 + 1))
+    return out
+
+
+@dataclass
+class Design:
+    lef: Lef
+    deff: Def
+    guides: dict
+
+    @classmethod
+    def load(cls, lef_path: str, def_path: str, guide_path: str | None = None) -> "Design":
+        return cls(parse_lef(lef_path), parse_def(def_path), parse_guide(guide_path) if guide_path else {})
+
+
+def extract_region(design: Design, route_box, *, ext: int = 2000, max_aps_per_pin: int = 3,
+                   boundary_pins: bool = True, union_tracks: bool = False,
+                   max_nets: int | None = None) -> tuple[Geometry, Instance]:
+    """Region instance of ``route_box = (x0, y0, x1, y1)`` (DBU), grid over the box grown by ``ext``.
+
+    * grid: x tracks of the lowest vertical layer and y tracks of the lowest horizontal layer
+      inside the grown box (``union_tracks``: the union over all layers, as TritonRoute's grid
+      graph does -- non-uniform pitch);
+    * nets: every DEF net with >= 2 pins *in the region*, a pin being a component pin whose
+      shapes touch the route box or (``boundary_pins``) a point where one of the net's guide
+      rectangles crosses the box boundary, on the guide's layer; ids 1..n in DEF order
+      (``max_nets`` keeps the first ones, the others' pins turn into blockages);
+    * APs: up to ``max_aps_per_pin`` on-track crossings nearest to the pin's shapes;
+    * blockages: crossings within ``width/2 + spacing`` of a fixed shape (power rails, OBS,
+      pins of nets that are not routed here); an AP always wins over a blockage.
+    """
+    lef, d = design.lef, design.deff
+    bx0, by0, bx1, by1 = route_box
+    gx0, gy0, gx1, gy1 = bx0 - ext, by0 - ext, bx1 + ext, by1 + ext
+    Z = len(lef.layers)
+    lay_v = [l for l in lef.layers if l.direction == 1]
+    lay_h = [l for l in lef.layers if l.direction == 0]
+    xs, ys = set(), set()
+    for l in (lef.layers if union_tracks else lay_v[:1] or lef.layers[:1]):
+        xs |= _track_coords(d.tracks.get(l.name, {}).get("X", []), gx0, gx1)
+    for l in (lef.layers if union_tracks else lay_h[:1] or lef.layers[:1]):
+        ys |= _track_coords(d.tracks.get(l.name, {}).get("Y", []), gy0, gy1)
+    xc = np.array(sorted(xs), np.int64)
+    yc = np.array(sorted(ys), np.int64)
+    X, Y = len(xc), len(yc)
+    if X < 2 or Y < 2:
+        raise ValueError("route box holds fewer than two tracks per axis")
+    geom = Geometry(X=X, Y=Y, Z=Z, x_coords=xc.astype(np.int32), y_coords=yc.astype(np.int32),
+                    layer_dir=np.array([l.direction for l in lef.layers], np.uint8),
+                    layer_pitch=np.array([l.pitch for l in lef.layers], np.int32),
+                    layer_min_width=np.array([l.width for l in lef.layers], np.int32))
+
+    def crossings(rect, bloat):
+        """index ranges of the grid lines within ``bloat`` of ``rect``"""
+        x0, y0, x1, y1 = rect
+        i0, i1 = np.searchsorted(xc, x0 - bloat, "left"), np.searchsorted(xc, x1 + bloat, "right")
+        j0, j1 = np.searchsorted(yc, y0 - bloat, "left"), np.searchsorted(yc, y1 + bloat, "right")
+        return int(i0), int(i1), int(j0), int(j1)
+
+    # ---- component pins that lie in the grown box: die-coordinate rect lists
+    comp_pins = {}       # (comp, pin) -> (use, [(z, rect)])
+    fixed = []           # (z, rect) of OBS shapes
+    for cname, (macro, px, py, orient) in d.components.items():
+        m = lef.macros.get(macro)
+        if m is None:
+            continue
+        w, h = m.size
+        ow, oh = (h, w) if orient in ("W", "E", "FW", "FE") else (w, h)
+        if px > gx1 or py > gy1 or px + ow < gx0 or py + oh < gy0:
+            continue
+        for pname, pin in m.pins.items():
+            shapes = []
+            for layer, *r in pin["rects"]:
+                z = lef.layer_index(layer)
+                if z >= 0:
+                    shapes.append((z, _orient(r, m.size, (px, py), orient)))
+            comp_pins[(cname, pname)] = (pin["use"], shapes)
+        for layer, *r in m.obs:
+            z = lef.layer_index(layer)
+            if z >= 0:
+                fixed.append((z, _orient(r, m.size, (px, py), orient)))
+
+    def touches_box(shapes):
+        return any(r[0] <= bx1 and r[2] >= bx0 and r[1] <= by1 and r[3] >= by0 for _, r in shapes)
+
+    # ---- region nets
+    region = []          # (net name, [pin descriptors]); descriptor = ("comp", key) | ("bnd", (i, j, z))
+    used_pins = set()
+    for nname, conns in d.nets.items():
+        pins = []
+        for key in conns:
+            cp = comp_pins.get(key)
+            if cp is not None and cp[0] == "SIGNAL" and touches_box(cp[1]):
+                pins.append(("comp", key))
+        if boundary_pins:
+            seen = set()
+            for (x0, y0, x1, y1, layer) in design.guides.get(nname, ()):
+                z = lef.layer_index(layer)
+                if z < 0 or x0 >= bx1 or x1 <= bx0 or y0 >= by1 or y1 <= by0:
+                    continue
+                ox0, oy0, ox1, oy1 = max(x0, bx0), max(y0, by0), min(x1, bx1), min(y1, by1)
+                cand = []
+                if x0 < bx0: cand.append((bx0, (oy0 + oy1) // 2))
+                if x1 > bx1: cand.append((bx1, (oy0 + oy1) // 2))
+                if y0 < by0: cand.append(((ox0 + ox1) // 2, by0))
+                if y1 > by1: cand.append(((ox0 + ox1) // 2, by1))
+                for (qx, qy) in cand:
+                    # nearest crossing inside the route box
+                    ii = np.nonzero((xc >= bx0) & (xc <= bx1))[0]
+                    jj = np.nonzero((yc >= by0) & (yc <= by1))[0]
+                    if len(ii) == 0 or len(jj) == 0:
+                        continue
+                    i = int(ii[np.argmin(np.abs(xc[ii] - qx))])
+                    j = int(jj[np.argmin(np.abs(yc[jj] - qy))])
+                    if (i, j, z) not in seen:
+                        seen.add((i, j, z))
+                        pins.append(("bnd", (i, j, z)))
+        if len(pins) >= 2:
+            region.append((nname, pins))
+    if max_nets is not None:
+        region = region[:max_nets]
+    for _, pins in region:
+        used_pins.update(k for kind, k in pins if kind == "comp")
+
+    # ---- blockages from fixed shapes
+    block = np.zeros((Z, Y, X), bool)
+    def block_shape(z, rect):
+        l = lef.layers[z]
+        i0, i1, j0, j1 = crossings(rect, l.width // 2 + l.spacing)
+        block[z, j0:j1, i0:i1] = True
+    for z, r in fixed:
+        block_shape(z, r)
+    for key, (use, shapes) in comp_pins.items():
+        if key in used_pins:
+            continue
+        for z, r in shapes:
+            block_shape(z, r)
+
+    # ---- access points
+    taken = np.zeros((Z, Y, X), bool)
+    ap_net, ap_pin, ap_xyz = [], [], []
+    kept = []
+    for nname, pins in region:
+        net_aps = []
+        for kind, key in pins:
+            cells = []
+            if kind == "bnd":
+                i, j, z = key
+                if not taken[z, j, i]:
+                    cells = [(i, j, z)]
+            else:
+                cand = []
+                for z, r in comp_pins[key][1]:
+                    l = lef.layers[z]
+                    i0, i1, j0, j1 = crossings(r, max(l.pitch, 1))
+                    for j in range(j0, j1):
+                        for i in range(i0, i1):
+                            if taken[z, j, i]:
+                                continue
+                            ddx = max(r[0] - xc[i], 0, xc[i] - r[2])
+                            ddy = max(r[1] - yc[j], 0, yc[j] - r[3])
+                            cand.append((int(ddx + ddy), z, j, i))
+                cand.sort()
+                for _, z, j, i in cand:
+                    if (i, j, z) not in cells:
+                        cells.append((i, j, z))
+                    if len(cells) >= max_aps_per_pin:
+                        break
+            if cells:
+                for (i, j, z) in cells:
+                    taken[z, j, i] = True
+                net_aps.append(cells)
+        if len(net_aps) >= 2:
+            kept.append(nname)
+            nid = len(kept)
+            for p, cells in enumerate(net_aps, 1):
+                for (i, j, z) in cells:
+                    ap_net.append(nid); ap_pin.append(p); ap_xyz.append((i, j, z))
+        else:
+            for cells in net_aps:
+                for (i, j, z) in cells:
+                    taken[z, j, i] = False
+                    block[z, j, i] = True
+    ap_xyz = np.asarray(ap_xyz, np.int32).reshape(-1, 3)
+    if len(ap_xyz):
+        block[ap_xyz[:, 2], ap_xyz[:, 1], ap_xyz[:, 0]] = False
+    bz, by, bx = np.nonzero(block)
+    inst = Instance(
+        block_xyz=np.stack([bx, by, bz], 1).astype(np.int32).reshape(-1, 3),
+        ap_net=np.asarray(ap_net, np.int32), ap_pin=np.asarray(ap_pin, np.int32), ap_xyz=ap_xyz,
+        meta={"route_box": tuple(int(v) for v in route_box), "ext": ext, "net_names": kept,
+              "union_tracks": union_tracks},
+    )
+    return geom, inst
+
+
+# ------------------------------------------------------------------ fixtures (npz) round trip
+def save_regions(path: str, regions: dict) -> None:
+    """``regions``: name -> (Geometry, Instance).  Plain arrays only, so the fixtures travel
+    without the design files (tests/golden/ispd18_test1_regions.npz)."""
+    out = {}
+    for name, (g, inst) in regions.items():
+        out[f"{name}/x_coords"] = g.x_coords; out[f"{name}/y_coords"] = g.y_coords
+        out[f"{name}/layer_dir"] = g.layer_dir; out[f"{name}/layer_pitch"] = g.layer_pitch
+        out[f"{name}/layer_min_width"] = g.layer_min_width
+        out[f"{name}/block_xyz"] = inst.block_xyz; out[f"{name}/ap_net"] = inst.ap_net
+        out[f"{name}/ap_pin"] = inst.ap_pin; out[f"{name}/ap_xyz"] = inst.ap_xyz
+        out[f"{name}/route_box"] = np.asarray(inst.meta.get("route_box", (0, 0, 0, 0)), np.int64)
+    np.savez_compressed(path, **out)
+
+
+def load_regions(path: str) -> dict:
+    z = np.load(path)
+    names = sorted({k.split("/")[0] for k in z.files})
+    regions = {}
+    for n in names:
+        xc, yc = z[f"{n}/x_coords"], z[f"{n}/y_coords"]
+        g = Geometry(X=len(xc), Y=len(yc), Z=len(z[f"{n}/layer_dir"]), x_coords=xc, y_coords=yc,
+                     layer_dir=z[f"{n}/layer_dir"], layer_pitch=z[f"{n}/layer_pitch"],
+                     layer_min_width=z[f"{n}/layer_min_width"])
+        inst = Instance(block_xyz=z[f"{n}/block_xyz"], ap_net=z[f"{n}/ap_net"], ap_pin=z[f"{n}/ap_pin"],
+                        ap_xyz=z[f"{n}/ap_xyz"], meta={"route_box": tuple(int(v) for v in z[f"{n}/route_box"])})
+        regions[n] = (g, inst)
+    return regions
