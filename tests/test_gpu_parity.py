@@ -61,8 +61,8 @@ def test_episode_small_grids(shape):
 
 
 @pytest.mark.parametrize("kw", [dict(window_margin=-1), dict(window_margin=1), dict(window_margin=3, min_cluster=2),
-                                dict(min_cluster=4), dict(min_cluster=8), dict(window_margin=30)],
-                         ids=["global-only", "margin1-fallbacks", "margin3-c2", "c4", "c8", "margin30"])
+                                dict(min_cluster=4), dict(min_cluster=8), dict(min_cluster=16), dict(window_margin=30)],
+                         ids=["global-only", "margin1-fallbacks", "margin3-c2", "c4", "c8", "c16", "margin30"])
 def test_route_paths_agree_across_engines(kw):
     """Window kernel (every cluster size), forced fall-backs to the full-grid sweeps and the
     full-grid path alone must all reproduce the oracle bit-exactly."""

@@ -23,6 +23,7 @@
 static std::string g_create_error;
 
 #define XR_NG 3   // post-route groups
+#define XR_NB 5   // cluster-size buckets of the window kernel: 1, 2, 4, 8, 16 CTAs
 struct ProfEvent { int cls; cudaEvent_t a, b; cudaEvent_t step; int grp; };
 
 struct XrEnv {
@@ -49,8 +50,8 @@ struct XrEnv {
     // window-resident route kernel
     int win_margin = 14, min_cluster = 0, smem_cap = 0, n_sm = 148;
     std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
-    int32_t *p_lists = nullptr;         // pinned [2 + 4*XR_NG][N]: mode, group, env lists of the XR_NG x 4 cluster buckets
-    int32_t *d_lists = nullptr;         // device [4*XR_NG][N]
+    int32_t *p_lists = nullptr;         // pinned [2 + XR_NB*XR_NG][N]: mode, group, env lists of the XR_NG x XR_NB cluster buckets
+    int32_t *d_lists = nullptr;         // device [XR_NB*XR_NG][N]
     cudaStream_t gs[XR_NG] = {nullptr, nullptr, nullptr};   // one stream per post-route group
     cudaEvent_t ev_fork = nullptr, ev_join[XR_NG] = {nullptr, nullptr, nullptr};
     int grp_pins[XR_NG] = {0, 4, 8};    // group g = nets with at least grp_pins[g] pins (light / medium / heavy)
@@ -249,7 +250,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * 4 * XR_NG); DA(d.dbg, 16);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * XR_NB * XR_NG); DA(d.dbg, 16);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -268,7 +269,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
         cudaMallocHost(&env->p_full, N) != cudaSuccess ||
-        cudaMallocHost(&env->p_lists, sizeof(int32_t) * (2 + 4 * XR_NG) * N) != cudaSuccess) {
+        cudaMallocHost(&env->p_lists, sizeof(int32_t) * (2 + XR_NB * XR_NG) * N) != cudaSuccess) {
         xr_free(env);
         return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
     }
@@ -282,7 +283,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_netwin.assign(N * (g.max_nets + 1) * 2, 0);
     env->win_margin = cfg->window_margin == 0 ? 14 : cfg->window_margin;
     // 0 = auto: per step, as many CTAs per environment as keeps about two clusters per SM's worth
-    env->min_cluster = cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2
+    env->min_cluster = cfg->min_cluster >= 16 ? 16 : cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2
                      : cfg->min_cluster == 1 ? 1 : 0;
     cudaDeviceGetAttribute(&env->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     cudaDeviceGetAttribute(&env->smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -290,6 +291,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     cudaFuncSetAttribute(k_route_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int k = 0; k < XR_NG; k++) {
@@ -557,7 +560,8 @@ static cudaError_t launch_win_t(XrEnv *env, cudaStream_t st, int n_envs, const i
 static int launch_route_win(XrEnv *env, cudaStream_t st, int C, int n_envs, const int *list) {
     Launch L(env, XR_K_ROUTE_WIN, st);
     cudaError_t e = C == 1 ? launch_win_t<1>(env, st, n_envs, list) : C == 2 ? launch_win_t<2>(env, st, n_envs, list)
-                  : C == 4 ? launch_win_t<4>(env, st, n_envs, list) : launch_win_t<8>(env, st, n_envs, list);
+                  : C == 4 ? launch_win_t<4>(env, st, n_envs, list) : C == 8 ? launch_win_t<8>(env, st, n_envs, list)
+                  : launch_win_t<16>(env, st, n_envs, list);
     if (e != cudaSuccess) { env->err = std::string("k_route_win launch: ") + cudaGetErrorString(e); return XR_E_CUDA; }
     return XR_OK;
 }
@@ -591,8 +595,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         cudaEventRecord(e, st);
         env->cur_step_ev = e; env->step_evs.push_back(e);
     }
-    static const int CS[4] = {1, 2, 4, 8};
-    int nb[XR_NG][4] = {};
+    static const int CS[XR_NB] = {1, 2, 4, 8, 16};
+    int nb[XR_NG][XR_NB] = {};
     int min_cluster = env->min_cluster;
     if (min_cluster == 0) {
         int n_route = 0;
@@ -603,7 +607,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     }
     bool any_global = false;
     int n_grp[XR_NG] = {};
-    int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then 4*XR_NG lists of N: [group][bucket]
+    int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then XR_NB*XR_NG lists of N: [group][bucket]
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
         int route = 0, mode = 0, grp = 0;
@@ -615,7 +619,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             int bucket = -1;
             const int mc = (np >= env->grp_pins[XR_NG - 1] && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
             if (WX > 0) {
-                for (int b = 0; b < 4 && bucket < 0; b++) {
+                for (int b = 0; b < XR_NB && bucket < 0; b++) {
                     if (CS[b] < mc) continue;
                     const int H = (WY + CS[b] - 1) / CS[b];
                     const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX));
@@ -626,7 +630,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (bucket < 0) grp = XR_NG - 1;
             if (bucket >= 0) {
                 mode = 1;
-                env->p_lists[(size_t)(2 + grp * 4 + bucket) * g.N + nb[grp][bucket]++] = i;
+                env->p_lists[(size_t)(2 + grp * XR_NB + bucket) * g.N + nb[grp][bucket]++] = i;
                 env->n_win_nets++;
             } else { any_global = true; env->n_global_nets++; }
         }
@@ -638,7 +642,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     CK(cudaMemcpyAsync(env->d.mode, modes, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(env->d.grp, grps, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     if (any_route) {
-        CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * 4 * XR_NG * g.N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * XR_NB * XR_NG * g.N, cudaMemcpyHostToDevice, st));
         Launch L(env, XR_K_ROUTE_BEGIN, st);
         k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d);
     }
@@ -663,9 +667,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         cudaStream_t sg = split ? env->gs[grp] : st;
         env->cur_grp = grp;
         if (split) CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
-        for (int b = 0; b < 4; b++) {
+        for (int b = XR_NB - 1; b >= 0; b--) {              // widest clusters first: they need a whole GPC
             if (!nb[grp][b]) continue;
-            int rc = launch_route_win(env, sg, CS[b], nb[grp][b], env->d_lists + (size_t)(grp * 4 + b) * g.N);
+            int rc = launch_route_win(env, sg, CS[b], nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);
             if (rc != XR_OK) return rc;
         }
         if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }

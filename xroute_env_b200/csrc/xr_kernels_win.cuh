@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     uint32_t *s_tloc = aux; aux += WIN_TGT_CAP;             // cell index of the unconnected APs inside this band
     uint32_t *s_red = aux; aux += 8;                        // [parity][0] smallest distance written, [1] best target in band, [4] #local targets
     c.cnt = &s_flag[5];
+#ifdef WIN_PHASE_CRIT
+    uint32_t *s_ph = aux; aux += 8;                         // this rank's phase times of the iteration (diagnostics)
+#endif
     c.rowd = reinterpret_cast<uint8_t *>(aux);
     c.cold = c.rowd + c.Z * H;
     c.posd = c.cold + c.Z * WX;
@@ -411,6 +414,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
 #ifdef WIN_PHASE_TIMING
     long long ph[7] = {0, 0, 0, 0, 0, 0, 0};
 #endif
+#ifdef WIN_PHASE_CRIT
+    long long phc[6] = {0, 0, 0, 0, 0, 0};
+#endif
     const long long tk0 = clock64();
     const bool open_x0 = wx0 > 0, open_x1 = wx0 + WX < g.X, open_y0 = wy0 > 0, open_y1 = wy0 + WY < g.Y;
     int parity = 0;
@@ -447,6 +453,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         for (;;) {
             n_iter++;
             if (tid == 0) { s_red[2 * parity] = 0xFFFFFFFFu; s_red[2 * parity + 1] = 0xFFFFFFFFu; }
+#ifdef WIN_PHASE_TIMING
+            const long long ph0 = clock64();
+#endif
             if (C > 1) {
                 // pull the neighbours' boundary rows into the halo rows
                 for (int i = tid; i < 2 * c.Z * WX; i += WIN_T) {
@@ -499,9 +508,29 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
 #ifdef WIN_PHASE_TIMING
             const long long p5 = clock64();
             ph[0] += p1 - p0; ph[1] += p2 - p1; ph[2] += p3 - p2; ph[3] += p4 - p3; ph[4] += p5 - p4;
-            ph[5] += ny; ph[6] += nx;
+            ph[5] += p0 - ph0;
+#endif
+#ifdef WIN_PHASE_CRIT
+            if (tid == 0) { s_ph[0] = (uint32_t)(p0 - ph0); s_ph[1] = (uint32_t)(p2 - p0); s_ph[2] = (uint32_t)(p4 - p2); s_ph[3] = (uint32_t)(p5 - p4); }
 #endif
             if (C > 1) cluster.sync(); else __syncthreads();
+#ifdef WIN_PHASE_TIMING
+            ph[6] += clock64() - p5;
+#endif
+#ifdef WIN_PHASE_CRIT
+            // critical path: per phase the slowest rank of the cluster (ph[0..3]), slowest / fastest rank total (ph[4], ph[5])
+            if (tid == 0 && rank == 0) {
+                uint32_t mx[4] = {0, 0, 0, 0}, tmax = 0, tmin = 0xFFFFFFFFu;
+                for (int r = 0; r < C; r++) {
+                    const uint32_t *q = (C > 1) ? cluster.map_shared_rank(s_ph, r) : s_ph;
+                    uint32_t tot = 0;
+                    for (int k = 0; k < 4; k++) { const uint32_t v = q[k]; mx[k] = v > mx[k] ? v : mx[k]; if (k) tot += v; }
+                    tmax = tot > tmax ? tot : tmax; tmin = tot < tmin ? tot : tmin;
+                }
+                for (int k = 0; k < 4; k++) phc[k] += mx[k];
+                phc[4] += tmax; phc[5] += tmin;
+            }
+#endif
             uint32_t gmin = 0xFFFFFFFFu, gB = 0xFFFFFFFFu;
             for (int r = 0; r < C; r++) {
                 const uint32_t *rr = (C > 1) ? cluster.map_shared_rank(&s_red[2 * parity], r) : &s_red[2 * parity];
@@ -751,14 +780,24 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         if (C > 1) cluster.sync(); else __syncthreads();
     }
     // relaxation accounting (cells touched by the in-window sweeps)
-    if (tid == 0 && rank == 0 && d.dbg) {
+#ifndef WIN_PHASE_RANK
+#define WIN_PHASE_RANK 0
+#endif
+#ifndef WIN_PHASE_MINC
+#define WIN_PHASE_MINC 1
+#endif
+    if (tid == 0 && rank == (C > WIN_PHASE_RANK ? WIN_PHASE_RANK : 0) && d.dbg) {
         atomicAdd(&d.dbg[0], (unsigned long long)n_iter); atomicAdd(&d.dbg[1], (unsigned long long)n_conn);
         atomicAdd(&d.dbg[2], (unsigned long long)cyc_relax); atomicAdd(&d.dbg[3], (unsigned long long)(clock64() - tk0));
         atomicAdd(&d.dbg[4], 1ull); atomicAdd(&d.dbg[5], (unsigned long long)(WX * WY));
         if (C == 8) { atomicAdd(&d.dbg[6], (unsigned long long)n_iter); atomicAdd(&d.dbg[7], (unsigned long long)cyc_relax);
                       atomicAdd(&d.dbg[15], (unsigned long long)n_conn); }
 #ifdef WIN_PHASE_TIMING
-        for (int k = 0; k < 7; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)ph[k]);
+#ifdef WIN_PHASE_CRIT
+        if (C >= WIN_PHASE_MINC) { for (int k = 0; k < 6; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)phc[k]); atomicAdd(&d.dbg[14], (unsigned long long)ph[6]); }
+#else
+        if (C >= WIN_PHASE_MINC) for (int k = 0; k < 7; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)ph[k]);
+#endif
 #endif
     }
     // relaxation accounting: cells actually touched by the dirty-line sweeps of this band

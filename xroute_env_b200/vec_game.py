@@ -235,7 +235,7 @@ class VecGame:
         _lib.check(self._L.xr_debug_counters(self._h, out), self._h)
         names = ["win_iterations", "win_connections", "win_relax_cycles", "win_kernel_cycles", "win_nets", "win_area",
                  "c8_iterations", "c8_relax_cycles", "ph_compact_y", "ph_sweep_y", "ph_compact_x", "ph_sweep_x",
-                 "ph_sweep_z", "lines_y", "lines_x", "c8_connections"]
+                 "ph_sweep_z", "ph_halo_pull", "ph_end_sync", "c8_connections"]
         return {k: int(out[i]) for i, k in enumerate(names) if k}
 
     def kernel_bench(self, which: str, reps: int = 10) -> dict:
