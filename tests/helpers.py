@@ -80,3 +80,65 @@ def brute_force_dist(geom, cflag, sources):
         if np.array_equal(nd, d):
             return d
         d = nd
+
+
+class OracleBackend:
+    """Simulator state for xroute_env_b200.wire.SimulatorServer backed by the CPU oracle
+    (test infrastructure: lets the wire layer be exercised without a GPU)."""
+
+    def __init__(self, geom, inst):
+        from oracle.oracle import OracleEnv
+        self.geom, self.inst = geom, inst
+        self.env = OracleEnv(geom, inst)
+        self.cum = [0, 0, 0]
+
+    def reset(self):
+        self.env.reset()
+        self.cum = [0, 0, 0]
+
+    def remaining(self):
+        return self.env.remaining()
+
+    def step(self, net_id):
+        m = self.env.step(int(net_id))
+        self.cum = [m["violation"], m["wirelength"], m["via"]]
+
+    def usage(self):
+        return self.env.state()[0]
+
+
+class WireClient:
+    """Agent side of the protocol with this repo's codec (what reference Game.reset/step do on
+    the wire, baseline_utils.py:392-481): REP socket for the data, REQ for the 'initial' request."""
+
+    def __init__(self, data_port, ctrl_port):
+        import zmq
+        self.zmq = zmq
+        self.ctx = zmq.Context()
+        self.rep = self.ctx.socket(zmq.REP)
+        self.rep.bind(f"tcp://127.0.0.1:{data_port}")
+        self.ctrl_port = ctrl_port
+
+    def reset(self):
+        from xroute_env_b200.wire import decode_message
+        req = self.ctx.socket(self.zmq.REQ)
+        req.setsockopt(self.zmq.LINGER, 0)
+        req.connect(f"tcp://127.0.0.1:{self.ctrl_port}")
+        req.send(b"initial")
+        kind, msg = decode_message(self.rep.recv())
+        req.close(0)
+        assert kind == "request"
+        return msg
+
+    def step(self, net_id):
+        from xroute_env_b200.wire import decode_message, encode_response
+        self.rep.send(encode_response(int(net_id) - 1))
+        kind, msg = decode_message(self.rep.recv())
+        assert kind == "request"
+        if msg["is_done"]:
+            self.rep.send(b"\0")
+        return msg
+
+    def close(self):
+        self.rep.close(0)
+        self.ctx.term()

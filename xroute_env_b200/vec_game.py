@@ -30,6 +30,7 @@ class VecGame:
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.geom = geom
+        self.insts = list(instances)
         self.n_envs = len(instances)
         self.device = device
         if max_nets is None:
@@ -87,6 +88,7 @@ class VecGame:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def load_instance(self, env_id: int, inst: Instance):
+        self.insts[env_id] = inst
         b = np.ascontiguousarray(inst.block_xyz, np.int32).reshape(-1)
         n = np.ascontiguousarray(inst.ap_net, np.int32)
         p = np.ascontiguousarray(inst.ap_pin, np.int32)
