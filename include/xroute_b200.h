@@ -96,7 +96,12 @@ enum { XR_BUF_OBS = 0,        /* float32 [N][obs_stride] (see xr_obs_layout)    
        XR_BUF_NREMAIN = 4,    /* int32   [N]                                                 */
        XR_BUF_LEGAL = 5,      /* uint8   [N][max_nets+1]  1 = net id still to route          */
        XR_BUF_STATS = 6,      /* int64   [XR_STATS_COUNT] per-handle sums for the all-reduce */
-       XR_BUF_REWARD = 7      /* float64 [N] -(500 dvio + 4 dvia + 0.5 dwl)                   */ };
+       XR_BUF_REWARD = 7,     /* float64 [N] -(500 dvio + 4 dvia + 0.5 dwl)                   */
+       XR_BUF_NETFEAT = 8     /* float32 [N][max_nets+1][22] per-net feature vectors of the A3C flavour
+                                 (baseline/A3C/utils.py:212-277): [0] half-perimeter of the AP box in point
+                                 coordinates, [1] nets with an AP inside that box, [2..17] layer flags,
+                                 [18] times routed since reset, [19..21] its last d_violation, d_wirelength,
+                                 d_via; row 0 and rows of absent nets are zero                        */ };
 
 /* XR_BUF_STATS slots (summed over this handle's environments; all-reduce with SUM) */
 enum { XR_S_STEPS = 0, XR_S_EPISODES = 1, XR_S_VIOLATION = 2, XR_S_WIRELENGTH = 3, XR_S_VIA = 4,

@@ -185,3 +185,37 @@ class OracleEnv:
         rc = lib().orc_distance_field(self._h, int(net), sp, len(s), out.ctypes.data_as(C.POINTER(C.c_uint32)))
         assert rc == 0
         return out.reshape(g.Z, g.Y, g.X)
+
+
+def net_features(geom, inst, count=None, delta=None) -> np.ndarray:
+    """CPU restatement of the A3C flavour's 22-feature per-net vectors
+    (/root/reference/baseline/A3C/utils.py:212-277), float64 [max_net+1, 22], row = net id:
+    [0] half-perimeter of the access points' box in point coordinates (x, y DBU, z = layer; :246),
+    [1] number of nets -- the net itself included, the loop at :250-256 never skips it -- with an
+    access point inside that box, [2..17] flag per layer (maze z) holding an access point (:259-262),
+    [18] count_map entry (:268), [19..21] metrics_delta entry (:270).  Test infrastructure only."""
+    nets = inst.net_ids
+    n_max = max(nets) if nets else 0
+    out = np.zeros((n_max + 1, 22), np.float64)
+    px = geom.x_coords.astype(np.int64)[inst.ap_xyz[:, 0]] if len(inst.ap_xyz) else np.zeros(0, np.int64)
+    py = geom.y_coords.astype(np.int64)[inst.ap_xyz[:, 1]] if len(inst.ap_xyz) else np.zeros(0, np.int64)
+    pz = inst.ap_xyz[:, 2].astype(np.int64) if len(inst.ap_xyz) else np.zeros(0, np.int64)
+    for n in nets:
+        m = inst.ap_net == n
+        x0, x1, y0, y1, z0, z1 = px[m].min(), px[m].max(), py[m].min(), py[m].max(), pz[m].min(), pz[m].max()
+        out[n, 0] = (x1 - x0) + (y1 - y0) + (z1 - z0)
+        inside = (px >= x0) & (px <= x1) & (py >= y0) & (py <= y1) & (pz >= z0) & (pz <= z1)
+        out[n, 1] = len(set(inst.ap_net[inside].tolist()))
+        for z in set(pz[m].tolist()):
+            if z < 16:
+                out[n, 2 + z] = 1
+        if count is not None:
+            out[n, 18] = count.get(n, 0)
+        if delta is not None:
+            out[n, 19:22] = delta.get(n, (0, 0, 0))
+    return out
+
+
+def order_cost(violation, wirelength, via) -> float:
+    """/root/reference/baseline/A3C/utils.py:195-196."""
+    return 0.5 * wirelength + 4 * via + 500 * violation

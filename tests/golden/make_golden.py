@@ -254,7 +254,58 @@ def make_game_episode():
     print("game_episode.npz: replies", replies, "ret1", out["ret1"], "ret2", out["ret2"])
 
 
+def make_a3c_features():
+    """22-feature per-net vectors of the A3C flavour: the reference's own ``Game.get_feature`` and
+    ``Game._cal_reward`` (baseline/A3C/utils.py:195-277) run on seeded regions.  The module imports a
+    generated protobuf file that the repository does not ship (compile_proto.sh output); it is
+    stubbed -- get_feature never touches it."""
+    import types
+    for name in ("openroad_api", "openroad_api.proto", "openroad_api.proto.net_ordering_pb2"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, os.path.join(REF, "baseline", "A3C"))
+    saved = sys.modules.pop("utils", None)
+    import utils as a3c
+    from xroute_env_b200.instances import export_data, ispd18_geometry, make_instance
+    rng = np.random.default_rng(99)
+    out = {}
+    cases = [(12, 10, 5, 5, 3), (25, 26, 9, 12, 4), (30, 8, 9, 7, 5), (9, 9, 2, 3, 6)]
+    for idx, (X, Y, Z, n_nets, seed) in enumerate(cases):
+        g = ispd18_geometry(X, Y, Z)
+        inst = make_instance(g, n_nets, seed)
+        data = export_data(g, inst, np.zeros((Z, Y, X), np.uint8))
+        some = [int(v) for v in rng.permutation(inst.net_ids)[: max(1, n_nets // 2)]]
+        count_map = {str(n): int(rng.integers(1, 4)) for n in some}
+        metrics_delta = {str(n): [int(rng.integers(0, 3)), int(rng.integers(0, 50000)), int(rng.integers(0, 30))] for n in some}
+        game = a3c.Game.__new__(a3c.Game)
+        game.observation = None
+        game.accessPoints = None
+        with contextlib.redirect_stdout(io.StringIO()):
+            feats = game.get_feature(data + [[], [], count_map, metrics_delta])
+        nets = sorted(feats)
+        k = f"c{idx}"
+        out[k + "_dims"] = np.array([X, Y, Z, n_nets, seed], np.int32)
+        out[k + "_nets"] = np.array(nets, np.int32)
+        out[k + "_feat"] = np.stack([feats[n] for n in nets]).astype(np.float64)
+        out[k + "_count"] = np.array([[int(n), c] for n, c in count_map.items()], np.int64)
+        out[k + "_delta"] = np.array([[int(n)] + v for n, v in metrics_delta.items()], np.int64)
+    costs = np.array([[0, 0, 0], [1, 1010, 2], [3, 123456, 77], [0, 5, 0]], np.int64)
+    game = a3c.Game.__new__(a3c.Game)
+    out["cost_in"] = costs
+    out["cost_out"] = np.array([game._cal_reward(list(c)) for c in costs], np.float64)
+    out["n_cases"] = np.array([len(cases)], np.int32)
+    np.savez_compressed(os.path.join(HERE, "a3c_features.npz"), **out)
+    if saved is not None:
+        sys.modules["utils"] = saved
+    print("a3c_features.npz:", len(cases), "cases; cost", out["cost_out"].tolist())
+
+
 if __name__ == "__main__":
-    make_obs_cases()
-    make_reward_vectors()
-    make_game_episode()
+    which = sys.argv[1:] or ["obs", "reward", "game", "a3c"]
+    if "obs" in which:
+        make_obs_cases()
+    if "reward" in which:
+        make_reward_vectors()
+    if "game" in which:
+        make_game_episode()
+    if "a3c" in which:
+        make_a3c_features()

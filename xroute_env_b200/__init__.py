@@ -10,11 +10,11 @@ from .instances import (Geometry, Instance, PRESETS, ispd18_geometry, make_batch
                         preset_geometry, export_data)
 
 __all__ = ["Geometry", "Instance", "PRESETS", "ispd18_geometry", "make_batch", "make_instance",
-           "preset_geometry", "export_data", "Game", "VecGame", "build_3Dgrid", "reward"]
+           "preset_geometry", "export_data", "Game", "VecGame", "build_3Dgrid", "reward", "a3c_reward"]
 
 
 def __getattr__(name):
-    if name in ("Game", "build_3Dgrid", "reward"):
+    if name in ("Game", "build_3Dgrid", "reward", "a3c_reward"):
         from . import game
         return getattr(game, name)
     if name == "VecGame":

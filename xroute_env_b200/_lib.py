@@ -18,7 +18,7 @@ XR_M_COUNT = 6
 XR_STATS_COUNT = 16
 XR_K_COUNT = 8
 (XR_BUF_OBS, XR_BUF_DELTA, XR_BUF_CUM, XR_BUF_DONE, XR_BUF_NREMAIN, XR_BUF_LEGAL, XR_BUF_STATS,
- XR_BUF_REWARD) = range(8)
+ XR_BUF_REWARD, XR_BUF_NETFEAT) = range(9)
 K_NAMES = ["obs", "metrics", "route_begin", "sweep_xz", "sweep_y", "control", "route_win", "misc"]
 STAT_NAMES = ["steps", "episodes", "violation", "wirelength", "via", "blocked", "shorted", "overflow",
               "reward_x2", "relax_passes", "cells_relaxed", "connections"]

@@ -250,7 +250,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * XR_NB * XR_NG); DA(d.dbg, 16);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * XR_NB * XR_NG); DA(d.dbg, 16); DA(d.netfeat, N * (g.max_nets + 1) * XR_NF);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -418,8 +418,44 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
             env->h_netwin[((size_t)env_id * (g.max_nets + 1) + net) * 2 + 1] = wy1 - wy0 + 1;
         }
     }
+    // static per-net features of the A3C observation (baseline/A3C/utils.py:236-262): half-perimeter of
+    // the AP bounding box in point coordinates (x, y in DBU, z = layer), number of nets (itself
+    // included) with an AP inside that box, one flag per layer holding an AP
+    std::vector<float> nfeat((size_t)(g.max_nets + 1) * XR_NF, 0.f);
+    {
+        std::vector<int> bx0(g.max_nets + 1), bx1(g.max_nets + 1), by0(g.max_nets + 1), by1(g.max_nets + 1),
+            bz0(g.max_nets + 1), bz1(g.max_nets + 1);
+        for (int net = 1; net <= g.max_nets; net++) {
+            const int s = nstart[net], t = nstart[net + 1];
+            if (s == t) continue;
+            int x0 = 1 << 30, x1 = -(1 << 30), y0 = 1 << 30, y1 = -(1 << 30), z0 = 1 << 30, z1 = -(1 << 30);
+            float *nf = &nfeat[(size_t)net * XR_NF];
+            for (int k = s; k < t; k++) {
+                x0 = std::min(x0, env->xc[sx[k]]); x1 = std::max(x1, env->xc[sx[k]]);
+                y0 = std::min(y0, env->yc[sy[k]]); y1 = std::max(y1, env->yc[sy[k]]);
+                z0 = std::min(z0, sz[k]); z1 = std::max(z1, sz[k]);
+                if (sz[k] < 16) nf[2 + sz[k]] = 1.f;
+            }
+            bx0[net] = x0; bx1[net] = x1; by0[net] = y0; by1[net] = y1; bz0[net] = z0; bz1[net] = z1;
+            nf[0] = (float)((x1 - x0) + (y1 - y0) + (z1 - z0));
+        }
+        for (int net = 1; net <= g.max_nets; net++) {
+            if (nstart[net] == nstart[net + 1]) continue;
+            int conflict = 0;
+            for (int o = 1; o <= g.max_nets; o++) {
+                bool in = false;
+                for (int k = nstart[o]; k < nstart[o + 1] && !in; k++) {
+                    const int px = env->xc[sx[k]], py = env->yc[sy[k]], pz = sz[k];
+                    in = px >= bx0[net] && px <= bx1[net] && py >= by0[net] && py <= by1[net] && pz >= bz0[net] && pz <= bz1[net];
+                }
+                conflict += in;
+            }
+            nfeat[(size_t)net * XR_NF + 1] = (float)conflict;
+        }
+    }
     const Dev &d = env->d;
     const size_t e = env_id;
+    CK(cudaMemcpy(d.netfeat + e * (g.max_nets + 1) * XR_NF, nfeat.data(), sizeof(float) * nfeat.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.cellinfo + e * g.cells_p, ci.data(), sizeof(uint32_t) * g.cells_p, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.apnet + e * g.cells_p, an.data(), sizeof(uint16_t) * g.cells_p, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.ap_cellp + e * g.max_aps, cellp.data(), sizeof(int32_t) * g.max_aps, cudaMemcpyHostToDevice));
@@ -818,9 +854,9 @@ extern "C" int xr_obs_dlpack(XrEnv *env, int32_t env_id, void **out) {
     return XR_OK;
 }
 
-static int buffer_info(XrEnv *env, int which, void **p, int *ndim, int64_t shape[2], uint8_t *code, uint8_t *bits) {
+static int buffer_info(XrEnv *env, int which, void **p, int *ndim, int64_t shape[3], uint8_t *code, uint8_t *bits) {
     const Geo &g = env->g; const Dev &d = env->d;
-    shape[0] = g.N; shape[1] = 1; *ndim = 1;
+    shape[0] = g.N; shape[1] = 1; shape[2] = 1; *ndim = 1;
     switch (which) {
     case XR_BUF_OBS: *p = d.obs; *ndim = 2; shape[1] = g.obs_stride; *code = kXrDLFloat; *bits = 32; break;
     case XR_BUF_DELTA: *p = d.delta; *ndim = 2; shape[1] = 3; *code = kXrDLInt; *bits = 32; break;
@@ -830,24 +866,25 @@ static int buffer_info(XrEnv *env, int which, void **p, int *ndim, int64_t shape
     case XR_BUF_LEGAL: *p = d.legal; *ndim = 2; shape[1] = g.max_nets + 1; *code = kXrDLUInt; *bits = 8; break;
     case XR_BUF_STATS: *p = d.stats; shape[0] = XR_STATS_COUNT; *code = kXrDLInt; *bits = 64; break;
     case XR_BUF_REWARD: *p = d.reward; *code = kXrDLFloat; *bits = 64; break;
+    case XR_BUF_NETFEAT: *p = d.netfeat; *ndim = 3; shape[1] = g.max_nets + 1; shape[2] = XR_NF; *code = kXrDLFloat; *bits = 32; break;
     default: return XR_E_INVALID;
     }
     return XR_OK;
 }
 extern "C" int xr_buffer_dlpack(XrEnv *env, int32_t which, void **out) {
     if (!env || !out) return XR_E_INVALID;
-    void *p; int ndim; int64_t shape[2]; uint8_t code, bits;
+    void *p; int ndim; int64_t shape[3]; uint8_t code, bits;
     if (buffer_info(env, which, &p, &ndim, shape, &code, &bits) != XR_OK) return fail(env, XR_E_INVALID, "unknown buffer");
-    const int64_t strides[2] = {ndim == 2 ? shape[1] : 1, 1};
+    const int64_t strides[3] = {ndim == 3 ? shape[1] * shape[2] : ndim == 2 ? shape[1] : 1, ndim == 3 ? shape[2] : 1, 1};
     *out = make_dl(env, p, ndim, shape, strides, code, bits);
     return XR_OK;
 }
 extern "C" int xr_buffer_ptr(XrEnv *env, int32_t which, void **dev_ptr, int64_t *n_bytes) {
     if (!env || !dev_ptr) return XR_E_INVALID;
-    void *p; int ndim; int64_t shape[2]; uint8_t code, bits;
+    void *p; int ndim; int64_t shape[3]; uint8_t code, bits;
     if (buffer_info(env, which, &p, &ndim, shape, &code, &bits) != XR_OK) return fail(env, XR_E_INVALID, "unknown buffer");
     *dev_ptr = p;
-    if (n_bytes) *n_bytes = shape[0] * (ndim == 2 ? shape[1] : 1) * (bits / 8);
+    if (n_bytes) *n_bytes = shape[0] * shape[1] * shape[2] * (bits / 8);
     return XR_OK;
 }
 

@@ -12,6 +12,7 @@
 
 #define XR_INF 0x3FFFFFFFu
 #define XR_ZMAX 16
+#define XR_NF 22        // features per net (baseline/A3C/utils.py:212-277)
 
 // cellinfo bits
 #define CI_OWNER_MASK 0x0000FFFFu
@@ -84,6 +85,7 @@ struct Dev {
     long long *envstat;   // [N][8] steps, episodes, pumps, connections, sum dvio, sum dwl, sum dvia, cells relaxed; [2] counts relaxation passes
     long long *stats;     // [16]
     unsigned long long *dbg; // [8] window-kernel diagnostics: iterations, connections, relax cycles, kernel cycles, nets, window cells
+    float    *netfeat;    // [N][max_nets+1][XR_NF] per-net feature vector (A3C flavour): HPWL, bbox conflicts, 16 layer flags | count, last d_vio, d_wl, d_via
     uint8_t  *obs_do;     // [N]
     uint8_t  *obs_full;   // [N] reset: 1 = full observation build, 0 = incremental (buffer invariant holds)
     float    *obs;        // [N][obs_stride]

@@ -256,6 +256,10 @@ __global__ void k_finalize(Geo g, Dev d, int pass) {
     const long long vio = blocked + shorted, wl = d.wlvia[2 * env], via = d.wlvia[2 * env + 1];
     const long long dv = vio - cum[0], dw = wl - cum[1], da = via - cum[2];
     d.delta[3 * env] = (int)dv; d.delta[3 * env + 1] = (int)dw; d.delta[3 * env + 2] = (int)da;
+    {   // dynamic part of the routed net's feature vector: times routed, its last deltas
+        float *nf = d.netfeat + ((size_t)env * (g.max_nets + 1) + raw) * XR_NF;
+        nf[18] += 1.f; nf[19] = (float)dv; nf[20] = (float)dw; nf[21] = (float)da;
+    }
     cum[0] = vio; cum[1] = wl; cum[2] = via; cum[3] = blocked; cum[4] = shorted; cum[5] = overflow;
     double r = -1.0;
     r *= (double)dv * 500 + (double)da * 4 + (double)dw * 0.5;
@@ -291,6 +295,10 @@ __global__ void k_reset_env(Geo g, Dev d) {
     if (env >= g.N || !d.obs_do[env]) return;
     uint8_t *routed = d.routed + (size_t)env * (g.max_nets + 1);
     for (int k = 0; k <= g.max_nets; k++) routed[k] = 0;
+    for (int k = 0; k <= g.max_nets; k++) {
+        float *nf = d.netfeat + ((size_t)env * (g.max_nets + 1) + k) * XR_NF;
+        nf[18] = 0.f; nf[19] = 0.f; nf[20] = 0.f; nf[21] = 0.f;
+    }
     for (int k = 0; k < 6; k++) d.cum[6 * (size_t)env + k] = 0;
     d.wlvia[2 * env] = 0; d.wlvia[2 * env + 1] = 0;
     d.msum[4 * env] = 0; d.msum[4 * env + 1] = 0; d.msum[4 * env + 2] = 0;

@@ -32,6 +32,27 @@ def reward(violation, wirelength, via):
     return r
 
 
+def a3c_reward(openroad_cost, xroute_cost, action_list, total_step):
+    """Whole-order reward of the A3C flavour, evaluated as
+    ``/root/reference/baseline/A3C/utils.py:316-333`` does: cost of the default order minus cost of the
+    chosen order (``0.5*wl + 4*via + 500*vio`` each, on ``[violation, wirelength, via]``), minus the
+    mismatch penalty ``alpha/k * sum((a_i - i)^2)`` over the 0-based ``action_list`` with
+    ``alpha = 0.1`` for the first 100 steps.  Returns ``(reward, done)``; done = no violation left."""
+    cal = lambda c: 0.5 * c[1] + 4 * c[2] + 500 * c[0]
+    try:
+        r = cal(openroad_cost) - cal(xroute_cost)
+    except Exception:
+        r = 0
+    alpha = 0.1 if total_step <= 100 else 0
+    k = len(action_list)
+    penalty = 0
+    for i in range(k):
+        penalty += (action_list[i] - i) ** 2
+    r -= alpha / k * penalty
+    done = len(xroute_cost) > 0 and xroute_cost[0] == 0
+    return r, done
+
+
 class Game:
     """Game wrapper (reference-compatible, GPU-backed)."""
 

@@ -156,6 +156,33 @@ class VecGame:
     def reward(self) -> torch.Tensor:      # float64 [N]
         return self._buffer(_lib.XR_BUF_REWARD)
 
+    @property
+    def net_features(self) -> torch.Tensor:
+        """float32 [N, max_nets+1, 22] per-net feature vectors (row = net id) in the layout of the
+        reference's A3C flavour (``baseline/A3C/utils.py:212-277``): half-perimeter of the AP box,
+        nets with an AP inside it, 16 layer flags, times routed since reset, last d_violation /
+        d_wirelength / d_via.  Static part set at load, dynamic part updated by every step."""
+        return self._buffer(_lib.XR_BUF_NETFEAT)
+
+    def route_order(self, orders) -> torch.Tensor:
+        """Whole-order action of the A3C / MCTS flavours (``Response.net_list``,
+        ``baseline/xroute/net_ordering.proto:78``): reset, then route ``orders[k]`` (int32 [n, N],
+        0 = idle) as n back-to-back batched steps without reading anything back.  Returns the
+        cumulative metrics int64 [N, 6] view; the cost of an order is ``order_cost(cum)``."""
+        o = np.ascontiguousarray(orders, np.int32)
+        if o.ndim != 2 or o.shape[1] != self.n_envs:
+            raise ValueError(f"orders must have shape (n, {self.n_envs})")
+        self.reset()
+        for k in range(o.shape[0]):
+            self.step(o[k])
+        return self.cum
+
+    @staticmethod
+    def order_cost(cum: torch.Tensor) -> torch.Tensor:
+        """``0.5*wirelength + 4*via + 500*violation`` (``baseline/A3C/utils.py:195-196``), float64 [N]."""
+        c = cum.to(torch.float64)
+        return 0.5 * c[:, 1] + 4.0 * c[:, 2] + 500.0 * c[:, 0]
+
     def obs_batch(self) -> torch.Tensor:
         """float32 [N, max_channels, Z, Y, X] strided view of the whole observation block
         (channels beyond 2+7*n_remaining[e] of environment e are stale)."""
