@@ -417,6 +417,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
 #ifdef WIN_PHASE_CRIT
     long long phc[6] = {0, 0, 0, 0, 0, 0};
 #endif
+#ifdef WIN_PHASE_SPLIT
+    long long sp[6] = {0, 0, 0, 0, 0, 0};     // first connection: iterations, cycles; later connections: iterations, cycles; connections; post-relax cycles
+#endif
     const long long tk0 = clock64();
     const bool open_x0 = wx0 > 0, open_x1 = wx0 + WX < g.X, open_y0 = wy0 > 0, open_y1 = wy0 + WY < g.Y;
     int parity = 0;
@@ -450,6 +453,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         // read -- are final.  The remaining dirty lines stay flagged and are folded into
         // the next connection's iterations (or dropped when the net is done).
         const long long tr0 = clock64();
+#ifdef WIN_PHASE_SPLIT
+        const int sp_it0 = n_iter;
+#endif
         for (;;) {
             n_iter++;
             if (tid == 0) { s_red[2 * parity] = 0xFFFFFFFFu; s_red[2 * parity + 1] = 0xFFFFFFFFu; }
@@ -543,6 +549,10 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         // ---- best target in this band + window-exit test
         const long long tq0 = clock64();
         cyc_relax += tq0 - tr0; n_conn++;
+#ifdef WIN_PHASE_SPLIT
+        if (first) { sp[0] += n_iter - sp_it0; sp[1] += tq0 - tr0; } else { sp[2] += n_iter - sp_it0; sp[3] += tq0 - tr0; }
+        sp[4] += 1;
+#endif
         if (tid == 0) s_best[0] = ~0ull;
         __syncthreads();
         unsigned long long best = ~0ull;
@@ -756,6 +766,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
             }
         }
         if (C > 1) cluster.sync(); else __syncthreads();
+#ifdef WIN_PHASE_SPLIT
+        sp[5] += clock64() - tq0;           // target choice, exit test, backtrace, commit, pin bookkeeping
+#endif
         const int more = (C > 1) ? *cluster.map_shared_rank(&s_flag[3], 0) : s_flag[3];
         if (!more) break;
         if (first) {
@@ -793,7 +806,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         if (C == 8) { atomicAdd(&d.dbg[6], (unsigned long long)n_iter); atomicAdd(&d.dbg[7], (unsigned long long)cyc_relax);
                       atomicAdd(&d.dbg[15], (unsigned long long)n_conn); }
 #ifdef WIN_PHASE_TIMING
-#ifdef WIN_PHASE_CRIT
+#ifdef WIN_PHASE_SPLIT
+        if (C >= WIN_PHASE_MINC) { for (int k = 0; k < 6; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)sp[k]); }
+#elif defined(WIN_PHASE_CRIT)
         if (C >= WIN_PHASE_MINC) { for (int k = 0; k < 6; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)phc[k]); atomicAdd(&d.dbg[14], (unsigned long long)ph[6]); }
 #else
         if (C >= WIN_PHASE_MINC) for (int k = 0; k < 7; k++) atomicAdd(&d.dbg[8 + k], (unsigned long long)ph[k]);
