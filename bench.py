@@ -58,7 +58,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f,
+                                          "-lms", "25", "-i", str(self.idx)], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -184,6 +184,60 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def ispd_leg(device: int, cpu: bool, n_envs: int = 128, episodes: int = 3):
+    import torch
+    from xroute_env_b200 import VecGame
+    from xroute_env_b200.ispd import load_regions
+    name = "t1_7x7_y79800"
+    geom, inst = load_regions(os.path.join(ROOT, "tests", "golden", "ispd18_test1_regions.npz"))[name]
+    nets = inst.net_ids
+    rng = np.random.default_rng(SEED)
+    orders = np.stack([np.concatenate([rng.permutation(nets) for _ in range(episodes + 1)]) for _ in range(n_envs)], 1)
+    orders = np.ascontiguousarray(orders, np.int32)
+    vg = VecGame(geom, [inst] * n_envs, device=device)
+    t = 0
+    def episode():
+        nonlocal t
+        vg.reset()
+        for _ in range(len(nets)):
+            vg.step(orders[t]); t += 1
+    episode()                                            # warm-up episode
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(episodes):
+        episode()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"region": f"{name} (routeBox 39900,79800-79800,119700; {geom.X}x{geom.Y}x{geom.Z}, {len(nets)} nets, "
+                     f"{len(inst.ap_net)} access points, {len(inst.block_xyz)} blockages)",
+           "envs": n_envs, "value": episodes * len(nets) * n_envs / (ms / 1e3), "unit": "env-steps/s",
+           "ms_per_step": ms / (episodes * len(nets)), "route_paths": vg.route_counters()}
+    vg.close()
+    if cpu:
+        import ctypes as C
+        from oracle.oracle import OracleEnv, lib, build
+        build()
+        buf = np.empty((2 + 7 * len(nets), geom.cells), np.float32)
+        env = OracleEnv(geom, inst)
+        steps = 0
+        t0 = time.perf_counter()
+        for e in range(n_envs):
+            env.reset()
+            for net in orders[: len(nets), e]:
+                env.step(int(net))
+                lib().orc_obs(env._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.shape[0])
+                steps += 1
+            if time.perf_counter() - t0 > 8.0:
+                break
+        wall = time.perf_counter() - t0
+        out["cpu_port_1_thread"] = {"value": steps / wall, "unit": "env-steps/s",
+                                    "sample": f"{steps} env-steps (obs+route+reward, oracle/xr_oracle.c) in {wall:.1f}s"}
+        out["gpu_over_cpu_thread"] = out["value"] / (steps / wall)
+    return out
 
 
 # --------------------------------------------------------------------------- GPU side
@@ -369,6 +423,13 @@ def run_ours(args):
                                 "(17 GB/step on average); one episode of 32 steps"}
         vg2.close()
 
+    # BASELINE.json configs[0]/[2]: a real ispd18_test1 7x7-gcell region (extracted from the LEF/DEF/guide
+    # files, tests/golden/ispd18_test1_regions.npz), 128 environments of it with independent random net
+    # orders on the GPU, next to the CPU oracle routing the same region on one host thread
+    ispd = None
+    if rank == 0 and world == 1 and not args.no_ispd:
+        ispd = ispd_leg(local, cpu=not args.no_cpu)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle
@@ -407,6 +468,7 @@ def run_ours(args):
             "profiled_leg_ms_per_step": ms_prof / K,
             "cpu_baseline": cpu_baseline,
             "full_obs_rebuild": full_rebuild,
+            "ispd18_test1": ispd,
             "route_paths": route_paths,
             "episode_stats": stats,
         }
@@ -424,6 +486,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-full", action="store_true", help="skip the full-observation-rebuild comparison leg")
+    ap.add_argument("--no-ispd", action="store_true", help="skip the real ispd18_test1 region leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
