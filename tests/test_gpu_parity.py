@@ -106,6 +106,22 @@ def test_observation_modes_match_oracle(obs_mode):
     vg.close()
 
 
+@pytest.mark.parametrize("minc,cluster", [(2, 0), (2, 4), (8, 0), (16, 0)], ids=["dual-c2", "dual-c4", "dual-c8", "dual-c16"])
+def test_dual_cyclic_layout_kernel(minc, cluster, monkeypatch):
+    """Every net through the dual-layout window kernel (rows and columns dealt cyclically over the
+    cluster, lowered cells pushed between the two copies over DSMEM): bit-exact like the others,
+    including forced window escapes that hand a connection to the full-grid path."""
+    monkeypatch.setenv("XR_DUAL_PINS", "2")
+    monkeypatch.setenv("XR_DUAL_MINC", str(minc))
+    geom = ispd18_geometry(48, 44, 9)
+    insts = make_batch(geom, 5, 10, seed=900, p_obstacle=0.2)
+    _run_episode(geom, insts, seed=8, min_cluster=cluster)
+    _run_episode(geom, insts[:2], seed=9, min_cluster=cluster, window_margin=1)
+    geom = ispd18_geometry(90, 70, 9)
+    geom.x_coords = np.cumsum(np.random.default_rng(1).integers(100, 700, 90)).astype(np.int32)   # non-uniform pitch
+    _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, min_cluster=cluster, check_obs_every=4)
+
+
 def test_window_fallback_counter_and_exactness():
     from xroute_env_b200 import VecGame
     geom = ispd18_geometry(64, 64, 9)

@@ -11,6 +11,7 @@
 #include "xr_kernels_env.cuh"
 #include "xr_kernels_maze.cuh"
 #include "xr_kernels_win.cuh"
+#include "xr_kernels_win2.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -23,7 +24,7 @@
 static std::string g_create_error;
 
 #define XR_NG 3   // post-route groups
-#define XR_NB 5   // cluster-size buckets of the window kernel: 1, 2, 4, 8, 16 CTAs
+#define XR_NB 9   // launch buckets of the window kernels: band layout with 1, 2, 4, 8, 16 CTAs, then dual cyclic layout with 2, 4, 8, 16
 struct ProfEvent { int cls; cudaEvent_t a, b; cudaEvent_t step; int grp; };
 
 struct XrEnv {
@@ -56,6 +57,8 @@ struct XrEnv {
     cudaEvent_t ev_fork = nullptr, ev_join[XR_NG] = {nullptr, nullptr, nullptr};
     int grp_pins[XR_NG] = {0, 4, 8};    // group g = nets with at least grp_pins[g] pins (light / medium / heavy)
     int heavy_cluster = 8;              // minimum cluster size of the heaviest group (0 = same as the others)
+    int dual_pins = 8;                  // nets with at least this many pins use the dual cyclic layout (0 = never)
+    int dual_minc = 8;                  // ... on clusters of at least this many CTAs
     long long n_win_nets = 0, n_global_nets = 0;
     // counters
     long long n_launch = 0, n_sync = 0;
@@ -293,6 +296,11 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     cudaFuncSetAttribute(k_route_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
     cudaFuncSetAttribute(k_route_win<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(k_route_win2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_cap);
+    cudaFuncSetAttribute(k_route_win2<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int k = 0; k < XR_NG; k++) {
@@ -305,6 +313,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     if (const char *e = getenv("XR_MEDIUM_PINS")) env->grp_pins[1] = std::max(2, atoi(e));
     if (const char *e = getenv("XR_HEAVY_PINS")) env->grp_pins[2] = std::max(env->grp_pins[1], atoi(e));
     if (const char *e = getenv("XR_HEAVY_CLUSTER")) env->heavy_cluster = atoi(e);
+    if (const char *e = getenv("XR_DUAL_PINS")) env->dual_pins = atoi(e);
+    if (const char *e = getenv("XR_DUAL_MINC")) env->dual_minc = std::max(2, atoi(e));
     // dynamic shared memory of the x+z sweep
     const int smem = g.Z * g.Xp * 5;
     cudaFuncSetAttribute(k_sweep_xz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -593,8 +603,25 @@ static cudaError_t launch_win_t(XrEnv *env, cudaStream_t st, int n_envs, const i
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k_route_win<C>, env->g, env->d, list);
 }
-static int launch_route_win(XrEnv *env, cudaStream_t st, int C, int n_envs, const int *list) {
+template <int C>
+static cudaError_t launch_win2_t(XrEnv *env, cudaStream_t st, int n_envs, const int *list) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_envs * C)); cfg.blockDim = dim3(WIN_T);
+    cfg.dynamicSmemBytes = (size_t)env->smem_cap; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_route_win2<C>, env->g, env->d, list);
+}
+static int launch_route_win(XrEnv *env, cudaStream_t st, int C, bool dual, int n_envs, const int *list) {
     Launch L(env, XR_K_ROUTE_WIN, st);
+    if (dual) {
+        cudaError_t e = C == 2 ? launch_win2_t<2>(env, st, n_envs, list) : C == 4 ? launch_win2_t<4>(env, st, n_envs, list)
+                      : C == 8 ? launch_win2_t<8>(env, st, n_envs, list) : launch_win2_t<16>(env, st, n_envs, list);
+        if (e != cudaSuccess) { env->err = std::string("k_route_win2 launch: ") + cudaGetErrorString(e); return XR_E_CUDA; }
+        return XR_OK;
+    }
     cudaError_t e = C == 1 ? launch_win_t<1>(env, st, n_envs, list) : C == 2 ? launch_win_t<2>(env, st, n_envs, list)
                   : C == 4 ? launch_win_t<4>(env, st, n_envs, list) : C == 8 ? launch_win_t<8>(env, st, n_envs, list)
                   : launch_win_t<16>(env, st, n_envs, list);
@@ -631,7 +658,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         cudaEventRecord(e, st);
         env->cur_step_ev = e; env->step_evs.push_back(e);
     }
-    static const int CS[XR_NB] = {1, 2, 4, 8, 16};
+    static const int CS[XR_NB] = {1, 2, 4, 8, 16, 2, 4, 8, 16};
+    const int NB_BAND = 5;
     int nb[XR_NG][XR_NB] = {};
     int min_cluster = env->min_cluster;
     if (min_cluster == 0) {
@@ -654,8 +682,15 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
             int bucket = -1;
             const int mc = (np >= env->grp_pins[XR_NG - 1] && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
-            if (WX > 0) {
-                for (int b = 0; b < XR_NB && bucket < 0; b++) {
+            if (WX > 0 && env->dual_pins > 0 && np >= env->dual_pins) {
+                for (int b = NB_BAND; b < XR_NB && bucket < 0; b++) {
+                    if (CS[b] < mc || CS[b] < env->dual_minc) continue;
+                    const long long bytes = 4ll * ((long long)WIN2_CELL_WORDS(g.Z, CS[b], WX, WY) + WIN2_AUX_WORDS(g.Z, CS[b], WX, WY));
+                    if (bytes <= env->smem_cap) bucket = b;
+                }
+            }
+            if (WX > 0 && bucket < 0) {
+                for (int b = 0; b < NB_BAND && bucket < 0; b++) {
                     if (CS[b] < mc) continue;
                     const int H = (WY + CS[b] - 1) / CS[b];
                     const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX));
@@ -705,7 +740,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         if (split) CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
         for (int b = XR_NB - 1; b >= 0; b--) {              // widest clusters first: they need a whole GPC
             if (!nb[grp][b]) continue;
-            int rc = launch_route_win(env, sg, CS[b], nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);
+            int rc = launch_route_win(env, sg, CS[b], b >= NB_BAND, nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);
             if (rc != XR_OK) return rc;
         }
         if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
