@@ -39,6 +39,7 @@ struct XrEnv {
     // host mirrors
     std::vector<uint8_t> h_routed, h_has_ap, h_done, h_loaded, h_reset;
     std::vector<uint16_t> h_npins;      // distinct pins per net
+    std::vector<int32_t> h_naps;        // access points per net
     std::vector<int32_t> h_nrem;
     int32_t *p_act = nullptr;           // pinned [N][2]
     int32_t *p_flags = nullptr;         // pinned [2]
@@ -279,6 +280,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_routed.assign(N * (g.max_nets + 1), 0);
     env->h_has_ap.assign(N * (g.max_nets + 1), 0);
     env->h_npins.assign(N * (g.max_nets + 1), 0);
+    env->h_naps.assign(N * (g.max_nets + 1), 0);
     env->h_done.assign(N, 0); env->h_loaded.assign(N, 0); env->h_reset.assign(N, 0);
     env->h_nrem.assign(N, 0);
     env->h_clean.assign(N, 0);
@@ -391,6 +393,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
     uint16_t *npins = &env->h_npins[(size_t)env_id * (g.max_nets + 1)];
     memset(has_ap, 0, g.max_nets + 1);
     memset(npins, 0, sizeof(uint16_t) * (g.max_nets + 1));
+    std::fill(env->h_naps.begin() + (size_t)env_id * (g.max_nets + 1), env->h_naps.begin() + (size_t)(env_id + 1) * (g.max_nets + 1), 0);
     for (int k = 0; k < n_ap; k++) {
         for (int dir = 0; dir < 6; dir++) {
             const int x = sx[k] + DXs[dir], y = sy[k] + DYs[dir], z = sz[k] + DZs[dir];
@@ -408,6 +411,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
             if (k == s || pin[k] != pin[k - 1]) np++;
         }
         npins[net] = (uint16_t)std::min(np, 65535);
+        env->h_naps[(size_t)env_id * (g.max_nets + 1) + net] = t - s;
         const int cx2 = xmin + xmax, cy2 = ymin + ymax;
         long best = -1; int bp = 0;
         for (int k = s; k < t; k++) {
@@ -682,7 +686,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
             int bucket = -1;
             const int mc = (np >= env->grp_pins[XR_NG - 1] && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
-            if (WX > 0 && env->dual_pins > 0 && np >= env->dual_pins) {
+            if (WX > 0 && env->dual_pins > 0 && np >= env->dual_pins && WX < 1024 && WY < 1024 &&
+                env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= WIN_TGT_CAP) {
                 for (int b = NB_BAND; b < XR_NB && bucket < 0; b++) {
                     if (CS[b] < mc || CS[b] < env->dual_minc) continue;
                     const long long bytes = 4ll * ((long long)WIN2_CELL_WORDS(g.Z, CS[b], WX, WY) + WIN2_AUX_WORDS(g.Z, CS[b], WX, WY));

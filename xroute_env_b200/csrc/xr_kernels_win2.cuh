@@ -23,7 +23,7 @@
 #define WIN2_CELL_WORDS(Z, C, WX, WY) \
     ((Z) * (((WY) + (C) - 1) / (C)) * ((WX) | 1) + (Z) * (((WX) + (C) - 1) / (C)) * ((WY) | 1))
 #define WIN2_AUX_WORDS(Z, C, WX, WY)                                                                          \
-    (30 * (Z) + (WX) + 2 + (WY) + 2 + 64 + 3 * WIN_TGT_CAP +                                                   \
+    (30 * (Z) + (WX) + 2 + (WY) + 2 + 64 + 6 * WIN_TGT_CAP +                                                   \
      ((Z) * (((WY) + (C) - 1) / (C)) + (Z) * (((WX) + (C) - 1) / (C)) + (((WY) + (C) - 1) / (C)) * (WX)) / 4 + 3 + \
      ((Z) * ((((WY) + (C) - 1) / (C)) > (((WX) + (C) - 1) / (C)) ? (((WY) + (C) - 1) / (C)) : (((WX) + (C) - 1) / (C)))) / 2 + 2 + 8)
 
@@ -375,6 +375,11 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
     int *s_tgt = reinterpret_cast<int *>(aux); aux += 2 * WIN_TGT_CAP;
     uint32_t *s_tloc = aux; aux += WIN_TGT_CAP;             // layout-A index of the unconnected APs owned by this CTA
     uint32_t *s_red = aux; aux += 8;
+    uint32_t *s_apc = aux; aux += WIN_TGT_CAP;              // access point i of the net: lx | wy << 10 | z << 20
+    uint16_t *s_appin = reinterpret_cast<uint16_t *>(aux); aux += WIN_TGT_CAP / 2;
+    uint16_t *s_tidx = reinterpret_cast<uint16_t *>(aux); aux += WIN_TGT_CAP / 2;    // unconnected access points
+    uint8_t *s_apconn = reinterpret_cast<uint8_t *>(aux); aux += WIN_TGT_CAP / 4;
+    uint8_t *s_apon = reinterpret_cast<uint8_t *>(aux); aux += WIN_TGT_CAP / 4;
     c.cnt = &s_flag[5];
     c.rowd = reinterpret_cast<uint8_t *>(aux);
     c.cold = c.rowd + c.Z * c.HA;
@@ -426,16 +431,23 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
     }
     if (tid < 8) s_flag[tid] = 0;
     __syncthreads();
-    // ---- seeds: the source pin's access points, in the layouts that own them
+    // ---- the net's access points, cached on chip (the host sends a net here only if it has at most
+    // WIN_TGT_CAP of them): window cell, DBU position (exit-test heuristic), pin, connected flag
     const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
-    const int s = ns[net], t = ns[net + 1];
-    const size_t aoff = (size_t)env * g.max_aps;
+    const int s = ns[net], t = ns[net + 1], n_ap = t - s;
+    const size_t aoff = (size_t)env * g.max_aps + s;
     const unsigned srcpin = d.net_srcpin[(size_t)env * (g.max_nets + 1) + net];
-    for (int i = s + tid; i < t; i += WIN_T) {
-        if (d.ap_pin[aoff + i] != srcpin) continue;
-        atomicAdd(&s_flag[6], 1);
+    for (int i = tid; i < n_ap; i += WIN_T) {
         const int cp = d.ap_cellp[aoff + i];
-        const int x = cp % g.Xp - wx0, wy = (cp / g.Xp) % g.Y - wy0, z = cp / (g.Xp * g.Y);
+        const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
+        const unsigned pin = d.ap_pin[aoff + i];
+        s_apc[i] = (uint32_t)((gx - wx0) | ((gy - wy0) << 10) | (z << 20));
+        s_tgt[2 * i] = g.xc[gx]; s_tgt[2 * i + 1] = g.yc[gy];
+        s_appin[i] = (uint16_t)pin;
+        s_apconn[i] = pin == srcpin;
+        if (pin != srcpin) continue;
+        atomicAdd(&s_flag[6], 1);
+        const int x = gx - wx0, wy = gy - wy0;               // seeds, in the layouts that own them
         if ((wy & (C - 1)) == rank) {
             const int ya = wy >> LC;
             c.A[((size_t)z * c.HA + ya) * c.WXp + x] &= ~WMASK;
@@ -459,24 +471,20 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
     if (C > 1) cluster.sync(); else __syncthreads();
     const int n_src_ap = s_flag[6];
     for (;;) {                                            // ---- one connection per trip
+        // ---- targets: the unconnected access points (s_tidx), those this CTA owns in layout A (s_tloc)
         if (tid == 0) { s_flag[4] = 0; s_red[4] = 0; }
         __syncthreads();
-        for (int i = s + tid; i < t; i += WIN_T) {
-            if (d.ap_conn[aoff + i]) continue;
-            const int cp = d.ap_cellp[aoff + i];
-            const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
-            const int k = atomicAdd(&s_flag[4], 1);
-            if (k < WIN_TGT_CAP) { s_tgt[2 * k] = g.xc[gx]; s_tgt[2 * k + 1] = g.yc[gy]; }
-            const int wy = gy - wy0;
-            if ((wy & (C - 1)) == rank) {
-                const unsigned m = atomicAdd(&s_red[4], 1u);
-                if (m < WIN_TGT_CAP) s_tloc[m] = (uint32_t)(((size_t)z * c.HA + (wy >> LC)) * c.WXp + (gx - wx0));
-            }
+        for (int i = tid; i < n_ap; i += WIN_T) {
+            if (s_apconn[i]) continue;
+            const uint32_t pc = s_apc[i];
+            const int x = pc & 1023, wy = (pc >> 10) & 1023, z = pc >> 20;
+            s_tidx[atomicAdd(&s_flag[4], 1)] = (uint16_t)i;
+            if ((wy & (C - 1)) == rank)
+                s_tloc[atomicAdd(&s_red[4], 1u)] = (uint32_t)(((size_t)z * c.HA + (wy >> LC)) * c.WXp + x);
         }
         __syncthreads();
         const int n_tgt = s_flag[4];
         const int n_loc = (int)s_red[4];
-        const bool early = n_tgt <= WIN_TGT_CAP;
         const long long tr0 = clock64();
         for (;;) {                                        // ---- relax (bounded early stop as in the band kernel)
             n_iter++;
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             ch = __reduce_min_sync(0xFFFFFFFFu, ch);
             if (lane == 0 && ch != 0xFFFFFFFFu) atomicMin(&s_red[2 * parity], ch);
             __syncthreads();
-            if (early) {
+            {
                 uint32_t bl = 0xFFFFFFFFu;
                 for (int k = tid; k < n_loc; k += WIN_T) bl = xr_min(bl, c.A[s_tloc[k]] & WMASK);
                 bl = __reduce_min_sync(0xFFFFFFFFu, bl);
@@ -529,22 +537,21 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             }
             parity ^= 1;
             if (gmin == 0xFFFFFFFFu) break;
-            if (early && gB < WINF && gmin >= gB) break;
+            if (gB < WINF && gmin >= gB) break;
         }
         const long long tq0 = clock64();
         cyc_relax += tq0 - tr0; n_conn++;
-        // ---- best target among the access points this CTA owns in layout A
+        // ---- best target among the access points this CTA owns in layout A: argmin (dist, padded cell index)
         if (tid == 0) s_best[0] = ~0ull;
         __syncthreads();
         unsigned long long best = ~0ull;
-        for (int i = s + tid; i < t; i += WIN_T) {
-            if (d.ap_conn[aoff + i]) continue;
-            const int cp = d.ap_cellp[aoff + i];
-            const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
-            const int wy = gy - wy0;
+        for (int k = tid; k < n_tgt; k += WIN_T) {
+            const uint32_t pc = s_apc[s_tidx[k]];
+            const int x = pc & 1023, wy = (pc >> 10) & 1023, z = pc >> 20;
             if ((wy & (C - 1)) != rank) continue;
-            const uint32_t dv = c.A[((size_t)z * c.HA + (wy >> LC)) * c.WXp + gx - wx0] & WMASK;
-            const unsigned long long key = ((unsigned long long)dv << 32) | (unsigned)cp;
+            const uint32_t dv = c.A[((size_t)z * c.HA + (wy >> LC)) * c.WXp + x] & WMASK;
+            const unsigned cp = (unsigned)((z * g.Y + wy0 + wy) * g.Xp + wx0 + x);
+            const unsigned long long key = ((unsigned long long)dv << 32) | cp;
             best = key < best ? key : best;
         }
 #pragma unroll
@@ -579,17 +586,11 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                 const uint32_t dv = c.A[((size_t)z * c.HA + ya) * c.WXp + x] & WMASK;
                 if (dv >= WINF || dv > B) continue;
                 const int px = g.xc[wx0 + x], py = g.yc[wy0 + rank + C * ya];
-                uint32_t hmin;
-                if (n_tgt <= WIN_TGT_CAP) {
-                    hmin = 0xFFFFFFFFu;
-                    for (int j = 0; j < n_tgt; j++) {
-                        const uint32_t hh = (uint32_t)(abs(px - s_tgt[2 * j]) + abs(py - s_tgt[2 * j + 1]));
-                        hmin = hh < hmin ? hh : hmin;
-                    }
-                } else {
-                    const uint32_t hx = px < bx0 ? bx0 - px : (px > bx1 ? px - bx1 : 0);
-                    const uint32_t hy = py < by0 ? by0 - py : (py > by1 ? py - by1 : 0);
-                    hmin = hx + hy;
+                uint32_t hmin = 0xFFFFFFFFu;
+                for (int j = 0; j < n_tgt; j++) {
+                    const int a = s_tidx[j];
+                    const uint32_t hh = (uint32_t)(abs(px - s_tgt[2 * a]) + abs(py - s_tgt[2 * a + 1]));
+                    hmin = hh < hmin ? hh : hmin;
                 }
                 if (dv + hmin <= B) esc = true;
             }
@@ -614,7 +615,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             }
             break;
         }
-        // ---- canonical backtrace + commit by warp 0 of rank 0 (layout A read over DSMEM)
+        // ---- canonical backtrace by warp 0 of rank 0 (layout A read over DSMEM).  The walk only touches the
+        // on-chip copies and the path list; the global state (occupancy, observation bytes, tree flags) of all
+        // new path cells is committed afterwards in one parallel pass.
         if (rank == 0 && tid < 32) {
             int cp = (int)(best & 0xFFFFFFFFu);
             int cx = cp % g.Xp, cy = (cp / g.Xp) % g.Y, cz = cp / (g.Xp * g.Y);
@@ -626,6 +629,16 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             bool fail = false;
             auto inwin = [&](int x, int y, int z) {
                 return x >= wx0 && x < wx0 + WX && y >= wy0 && y < wy0 + WY && z >= 0 && z < g.Z;
+            };
+            int pend = 0;                                // cells waiting for their global commit (s_tloc is free here)
+            auto flush = [&]() {
+                __syncwarp();
+                for (int k = lane; k < pend; k += 32) {
+                    const uint32_t pc = s_tloc[k];
+                    commit_cell(g, d, env, net, wx0 + (int)(pc & 1023u), wy0 + (int)((pc >> 10) & 1023u), (int)(pc >> 20));
+                }
+                __syncwarp();
+                pend = 0;
             };
             for (;;) {
                 __syncwarp();
@@ -647,15 +660,16 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                     const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                     const int run = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
                     if (run > 0) {
+                        if (pend + 32 > WIN_TGT_CAP) flush();
                         if (lane < run) {
-                            commit_cell(g, d, env, net, ax, ay, az);
+                            s_tloc[pend + lane] = (uint32_t)((ax - wx0) | ((ay - wy0) << 10) | (az << 20));
                             win2_set_tree<C>(cluster, c, ax - wx0, ay - wy0, az, va);
                             if (pn + lane < g.path_cap) path[pn + lane] = (az * g.Y + ay) * g.X + ax;
                             if (last >= 4) via += 1;
                             else if (last < 2) wl += abs(g.xc[ax] - g.xc[bx]);
                             else wl += abs(g.yc[ay] - g.yc[by]);
                         }
-                        pn += run;
+                        pn += run; pend += run;
                         cx -= run * ddx; cy -= run * ddy; cz -= run * ddz;
                         continue;
                     }
@@ -673,55 +687,39 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                 if (m == 0u) { fail = true; break; }
                 const int dir = __ffs(m) - 1;
+                if (pend + 1 > WIN_TGT_CAP) flush();
                 if (lane == dir) {
-                    commit_cell(g, d, env, net, cx, cy, cz);
+                    s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
                     win2_set_tree<C>(cluster, c, cx - wx0, cy - wy0, cz, vc);
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                     if (dir >= 4) via += 1;
                     else if (dir < 2) wl += abs(g.xc[cx] - g.xc[px]);
                     else wl += abs(g.yc[cy] - g.yc[py]);
                 }
-                pn += 1;
+                pn += 1; pend += 1;
                 cx = __shfl_sync(0xFFFFFFFFu, px, dir);
                 cy = __shfl_sync(0xFFFFFFFFu, py, dir);
                 cz = __shfl_sync(0xFFFFFFFFu, pz, dir);
                 last = dir;
             }
-            if (!fail) {
+            if (!fail) {                                 // the cell the walk ended on joins the tree on the first connection only
+                if (first && pend + 1 > WIN_TGT_CAP) flush();
                 if (lane == 0) {
                     if (first) {
-                        commit_cell(g, d, env, net, cx, cy, cz);
+                        s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
                         win2_set_tree<C>(cluster, c, cx - wx0, cy - wy0, cz, *win2_cellA<C>(cluster, c, cx - wx0, cy - wy0, cz));
                     }
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                 }
                 pn += 1;
+                if (first) pend += 1;
             }
+            flush();
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 wl += __shfl_xor_sync(0xFFFFFFFFu, wl, off);
                 via += __shfl_xor_sync(0xFFFFFFFFu, via, off);
             }
-            __syncwarp();
-            __threadfence_block();
-            for (int i = s + lane; i < t; i += 32) {
-                if (d.ap_conn[aoff + i]) continue;
-                const unsigned pin = d.ap_pin[aoff + i];
-                bool on = false;
-                for (int j = i; j >= s && d.ap_pin[aoff + j] == pin && !on; j--)
-                    on = (d.cflag[eoff + d.ap_cellp[aoff + j]] & CF_TREE) != 0;
-                for (int j = i + 1; j < t && d.ap_pin[aoff + j] == pin && !on; j++)
-                    on = (d.cflag[eoff + d.ap_cellp[aoff + j]] & CF_TREE) != 0;
-                if (on) d.ap_conn[aoff + i] = 2;
-            }
-            __syncwarp();
-            bool left = false;
-            for (int i = s + lane; i < t; i += 32) {
-                uint8_t v = d.ap_conn[aoff + i];
-                if (v == 2) { d.ap_conn[aoff + i] = 1; v = 1; }
-                left |= (v == 0);
-            }
-            left = __any_sync(0xFFFFFFFFu, left);
             if (lane == 0) {
                 d.wlvia[2 * env] += wl; d.wlvia[2 * env + 1] += via;
                 d.path_n[env] = pn;
@@ -732,12 +730,29 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                 d.conn_n[env] = cn + 1;
                 d.envstat[8 * (size_t)env + 3] += 1;
                 if (fail) d.flags[1] = 3;
-                s_flag[3] = (left && !fail) ? 1 : 0;
-                __threadfence();
+                s_flag[3] = fail ? 0 : 1;
             }
         }
         if (C > 1) cluster.sync(); else __syncthreads();
-        const int more = (C > 1) ? *cluster.map_shared_rank(&s_flag[3], 0) : s_flag[3];
+        const int go_on = (C > 1) ? *cluster.map_shared_rank(&s_flag[3], 0) : s_flag[3];
+        // ---- pin bookkeeping, by every CTA on its own copy: a pin is connected once any of its access points is
+        // on the tree (tree bit of the on-chip cell); rank 0 mirrors the flags to global memory for a hand-over
+        for (int i = tid; i < n_ap; i += WIN_T) {
+            const uint32_t pc = s_apc[i];
+            s_apon[i] = s_apconn[i] ? 1 : (((*win2_cellA<C>(cluster, c, pc & 1023, (pc >> 10) & 1023, pc >> 20)) >> 31) & 1u);
+        }
+        __syncthreads();
+        bool left = false;
+        for (int i = tid; i < n_ap; i += WIN_T) {
+            if (s_apconn[i]) continue;
+            const unsigned pin = s_appin[i];
+            bool on = false;
+            for (int j = i; j >= 0 && s_appin[j] == pin && !on; j--) on = s_apon[j] != 0;
+            for (int j = i + 1; j < n_ap && s_appin[j] == pin && !on; j++) on = s_apon[j] != 0;
+            if (on) { s_apconn[i] = 1; if (rank == 0) d.ap_conn[aoff + i] = 1; }
+            else left = true;
+        }
+        const int more = __syncthreads_or(left) && go_on;
         if (!more) break;
         if (first) {
             // after the first connection only the path is the tree (see the band kernel)
@@ -760,10 +775,10 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                         if (y < WY && xb < c.wb) c.cold[z * c.WB + xb] = 1;
                     }
                 }
+                if (C > 1) cluster.sync(); else __syncthreads();  // nobody pushes into a copy that is still being rebuilt
             }
             first = false;
         }
-        if (C > 1) cluster.sync(); else __syncthreads();
     }
     if (tid == 0 && rank == 0 && d.dbg) {
         atomicAdd(&d.dbg[0], (unsigned long long)n_iter); atomicAdd(&d.dbg[1], (unsigned long long)n_conn);
