@@ -1,0 +1,70 @@
+"""BASELINE.json configs at their full single-GPU sizes (gpu-marked): bit-exact parity on a sample of the
+environments at every step, and size-independent properties on ALL of them -- the congestion metrics
+recomputed from the final occupancy state (a checksum of checksums), wirelength/via monotone, every net routed."""
+import numpy as np
+import pytest
+
+from xroute_env_b200.instances import make_batch, preset_geometry
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_full(preset, n_envs, n_nets, sample, seed, gen_kw=None, obs_cap=-1):
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    geom = preset_geometry(preset)
+    insts = make_batch(geom, n_envs, n_nets, seed, **(gen_kw or {}))
+    vg = VecGame(geom, insts, device=0, obs_max_nets=obs_cap)
+    vg.reset()
+    rng = np.random.default_rng(seed)
+    orders = np.stack([rng.permutation(i.net_ids) for i in insts], 1).astype(np.int32)     # [n_nets, n_envs]
+    oracles = {e: OracleEnv(geom, insts[e]) for e in sample}
+    prev = np.zeros((n_envs, 6), np.int64)
+    for t in range(n_nets):
+        vg.step(orders[t])
+        delta, done, cum = vg.results_host()
+        cum = cum.numpy().copy()
+        assert (cum[:, 1] >= prev[:, 1]).all() and (cum[:, 2] >= prev[:, 2]).all()          # wirelength, via only grow
+        assert (cum[:, 0] == cum[:, 3] + cum[:, 4]).all()                                    # violation = blocked + shorted
+        prev = cum
+        for e, orc in oracles.items():
+            m = orc.step(int(orders[t, e]))
+            assert [int(v) for v in cum[e]] == [m["violation"], m["wirelength"], m["via"], m["blocked"], m["shorted"],
+                                                 m["overflow"]], (preset, t, e)
+            oc, oo, ocost = orc.last_paths(); gc, go, gcost = vg.paths(e)
+            assert np.array_equal(oc, gc) and np.array_equal(ocost, gcost), (preset, t, e)
+    assert bool(vg.done.all()) and int(vg.n_remaining.sum()) == 0
+    # the metrics of every environment, recomputed on the host from its final occupancy
+    for e in range(n_envs):
+        usage, owner = vg.state(e)
+        inst = insts[e]
+        blk = np.zeros(usage.shape, bool)
+        if len(inst.block_xyz):
+            blk[inst.block_xyz[:, 2], inst.block_xyz[:, 1], inst.block_xyz[:, 0]] = True
+        apn = np.zeros(usage.shape, np.int64)
+        apn[inst.ap_xyz[:, 2], inst.ap_xyz[:, 1], inst.ap_xyz[:, 0]] = inst.ap_net
+        blocked = int(((usage > 0) & blk).sum())
+        shorted = int(((usage >= 2) | ((usage == 1) & (apn != 0) & (apn != owner))).sum())
+        overflow = int(np.maximum(usage.astype(np.int64) - 1, 0).sum())
+        assert [blocked, shorted, overflow] == [int(v) for v in prev[e, 3:6]], (preset, e)
+    for e in sample:
+        if obs_cap < 0:
+            assert np.array_equal(vg.obs_host(e).numpy(), oracles[e].obs()), (preset, e)
+        gu, go_ = vg.state(e); ou, oo_ = oracles[e].state()
+        assert np.array_equal(gu, ou) and np.array_equal(go_, oo_), (preset, e)
+    rc = vg.route_counters()
+    vg.close()
+    return rc
+
+
+def test_config2_syn256_64_envs_full_episode():
+    rc = _check_full("SYN-256", 64, 32, sample=(0, 21, 42, 63), seed=20260000)
+    assert rc["window_nets"] == 64 * 32 and rc["global_nets"] == 0
+
+
+def test_config3_t1_7x7_shard_512_envs_full_episode():
+    _check_full("T1-7x7", 512, 32, sample=(0, 100, 511), seed=31)
+
+
+def test_config5_t1_1x1_shard_1024_envs_full_episode():
+    _check_full("T1-1x1", 1024, 32, sample=(0, 7, 1023), seed=32, gen_kw={"max_degree": 6})
