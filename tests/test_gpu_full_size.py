@@ -68,3 +68,37 @@ def test_config3_t1_7x7_shard_512_envs_full_episode():
 
 def test_config5_t1_1x1_shard_1024_envs_full_episode():
     _check_full("T1-1x1", 1024, 32, sample=(0, 7, 1023), seed=32, gen_kw={"max_degree": 6})
+
+
+def test_config4_syn1024_congested_nets_on_and_off_chip():
+    """1024x1024x9, 128 nets clustered around hot spots (observation materialised for the first 8 nets only):
+    windows up to 540x540 do not fit a cluster's shared memory, so this exercises the 16-CTA bucket and the
+    full-grid HBM sweeps next to the on-chip kernels -- all bit-exact against the oracle."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    geom = preset_geometry("SYN-1024")
+    insts = make_batch(geom, 2, 128, 777, hot_spots=16, hot_sigma=32.0)
+    vg = VecGame(geom, insts, device=0, obs_max_nets=8)
+    vg.reset()
+    oracles = [OracleEnv(geom, i) for i in insts]
+    # pick nets of very different extents: the largest and the smallest windows of each environment first
+    def extent(inst, n):
+        xy = inst.ap_xyz[inst.ap_net == n][:, :2]
+        return int((xy.max(0) - xy.min(0)).sum())
+    orders = []
+    for inst in insts:
+        ids = sorted(inst.net_ids, key=lambda n: -extent(inst, n))
+        orders.append(ids[:3] + ids[-3:])
+    for t in range(6):
+        acts = np.array([o[t] for o in orders], np.int32)
+        vg.step(acts)
+        delta, done, cum = vg.results_host()
+        for e, orc in enumerate(oracles):
+            m = orc.step(int(acts[e]))
+            assert [int(v) for v in cum[e]] == [m["violation"], m["wirelength"], m["via"], m["blocked"], m["shorted"],
+                                                 m["overflow"]], (t, e)
+            oc, oo, ocost = orc.last_paths(); gc, go, gcost = vg.paths(e)
+            assert np.array_equal(oc, gc) and np.array_equal(ocost, gcost), (t, e)
+    rc = vg.route_counters()
+    assert rc["global_nets"] >= 1 and rc["window_nets"] >= 1, rc
+    vg.close()
