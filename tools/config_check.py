@@ -21,7 +21,7 @@ def run(name):
     t0 = time.time()
     insts = make_batch(geom, n_envs, n_nets, 777, **kw)
     t_gen = time.time() - t0
-    vg = VecGame(geom, insts, device=0, obs_max_nets=cap)
+    vg = VecGame(geom, insts, device=0, obs_max_nets=cap, pumps_per_sync=int(os.environ.get("XR_PUMPS", "0")))
     vg.reset()
     rng = np.random.default_rng(1)
     orders = np.stack([rng.permutation(i.net_ids) for i in insts], 1).astype(np.int32)   # [n_nets, n_envs]
@@ -48,7 +48,7 @@ def run(name):
     dt = time.perf_counter() - t0
     print(f"{name}: {preset} {geom.X}x{geom.Y}x{geom.Z}, {n_envs} envs, {n_nets} nets, obs cap {cap}: parity OK on {n_par} envs x {n_chk} steps; "
           f"{n_steps} steps in {dt*1e3:.1f} ms -> {n_envs*n_steps/dt:.0f} env-steps/s ({dt/n_steps*1e3:.2f} ms/step); "
-          f"gen {t_gen:.1f}s; {vg.route_counters()}; mem {torch.cuda.mem_get_info()[0]/2**30:.1f} GiB free", flush=True)
+          f"gen {t_gen:.1f}s; {vg.route_counters()}; {vg.counters()}; mem {torch.cuda.mem_get_info()[0]/2**30:.1f} GiB free", flush=True)
     vg.close()
 
 if __name__ == "__main__":

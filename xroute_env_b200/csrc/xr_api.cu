@@ -249,6 +249,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.dist, N * g.cells_p); DA(d.cflag, N * g.cells_p);
     DA(d.act, N * 2); DA(d.phase, N); DA(d.changed, N); DA(d.reinit, N); DA(d.first, N);
     DA(d.ap_conn, N * g.max_aps); DA(d.flags, 4);
+    DA(d.g_rowd, N * g.Y); DA(d.g_rowf, N * g.Y); DA(d.g_slabd, N * g.Z * (g.Xp / 32)); DA(d.g_slabf, N * g.Z * (g.Xp / 32));
+    DA(d.g_cap, N); DA(d.g_gmin, N); DA(d.g_all, N);
     DA(d.msum, N * 4); DA(d.delta, N * 3); DA(d.cum, N * 6); DA(d.wlvia, N * 2); DA(d.done, N);
     DA(d.reward, N); DA(d.envstat, N * 8); DA(d.stats, XR_STATS_COUNT); DA(d.obs_do, N); DA(d.obs_full, N);
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
@@ -571,7 +573,7 @@ template <int CPL>
 static void launch_xz(XrEnv *env, cudaStream_t st) {
     const Geo &g = env->g;
     Launch L(env, XR_K_SWEEP_XZ, st);
-    k_sweep_xz<CPL><<<dim3(g.Y, g.N), dim3(32, g.Z), (size_t)g.Z * g.Xp * 5, st>>>(env->g, env->d);
+    k_sweep_xz<CPL><<<dim3((g.Y + XZ_ROWS - 1) / XZ_ROWS, g.N), dim3(32, g.Z), (size_t)g.Z * g.Xp * 5, st>>>(env->g, env->d);
 }
 static void launch_sweep_xz(XrEnv *env, cudaStream_t st) {
     const int cpl = (env->g.Xp + 31) / 32;

@@ -74,6 +74,13 @@ struct Dev {
     int32_t  *reinit;     // [N]
     int32_t  *first;      // [N]
     uint8_t  *ap_conn;    // [N][max_aps]
+    // full-grid path bookkeeping (xr_kernels_maze.cuh): dirty rows (consumed by the x+via sweep) and dirty
+    // (layer, 32-column slab)s (consumed by the y sweep); "deferred" twins for relaxations skipped by the cap
+    uint8_t  *g_rowd, *g_rowf;    // [N][Y]
+    uint8_t  *g_slabd, *g_slabf;  // [N][Z][Xp/32]
+    uint32_t *g_cap;      // [N] writes above this distance are skipped (best target distance known so far)
+    uint32_t *g_gmin;     // [N] smallest distance written in the current pump
+    int32_t  *g_all;      // [N] 1 = every row and slab counts as dirty in this pump (start, hand-over, re-init)
     int32_t  *flags;      // [0] envs in the global route loop, [1] error flag, [2] window fallbacks
     // results
     unsigned int *msum;   // [N][4] blocked, shorted, overflow

@@ -14,6 +14,13 @@
 //   k_control  : per environment, one warp: convergence test, target selection,
 //                canonical backtrace (32 cells of a straight run per memory round
 //                trip), commit, pin bookkeeping, next connection or finish.
+// Work is bounded three ways, none of which changes a result:
+//   dirty lines   a row is swept along x (and its via stacks relaxed) only if one of its cells changed since
+//                 its last sweep, a (layer, 32-column slab) along y likewise; blocks of clean lines exit at once;
+//   bounded stop  a connection's relaxation ends as soon as every distance written in a pump is >= the best
+//                 target distance (everything below it is final); pending dirty lines carry over;
+//   cap           a relaxation whose result exceeds the best target distance known so far is skipped and its
+//                 line flagged "deferred"; deferred lines turn dirty again when the next connection starts.
 // The fixpoint of the relaxations is unique, so the distance field equals
 // Dijkstra's regardless of sweep order; path identity rests on the canonical
 // backtrace rule shared with the oracle.
@@ -66,6 +73,13 @@ __global__ void k_seed(Geo g, Dev d) {
         d.conn_off[(size_t)env * (g.conn_cap + 1)] = 0;
     }
     if (net == 0) return;
+    // full-grid bookkeeping: the first pump of a net (or of a hand-over from a window kernel) sweeps everything
+    {
+        const int S = g.Xp / 32;
+        for (int i = threadIdx.x; i < g.Y; i += blockDim.x) { d.g_rowd[(size_t)env * g.Y + i] = 0; d.g_rowf[(size_t)env * g.Y + i] = 0; }
+        for (int i = threadIdx.x; i < g.Z * S; i += blockDim.x) { d.g_slabd[(size_t)env * g.Z * S + i] = 0; d.g_slabf[(size_t)env * g.Z * S + i] = 0; }
+        if (threadIdx.x == 0) { d.g_all[env] = 1; d.g_cap[env] = XR_INF; d.g_gmin[env] = 0xFFFFFFFFu; }
+    }
     const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
     const int s = ns[net], t = ns[net + 1];
     const unsigned srcpin = d.net_srcpin[(size_t)env * (g.max_nets + 1) + net];
@@ -100,15 +114,19 @@ __device__ __forceinline__ uint32_t wx_from_right(const Geo &g, int z, int x, ui
 
 // grid (Y, N), block (32, Z).  Warp z owns row (y, z); lane l owns CPL consecutive
 // cells starting at x0 = l*CPL.  Flags are kept 4 bits per cell in registers.
+#ifndef XZ_ROWS
+#define XZ_ROWS 1                    // rows per block (more: fewer launches of clean-row blocks, but a flood's rows serialise)
+#endif
 template <int CPL>
-__global__ void __launch_bounds__(32 * XR_ZMAX) k_sweep_xz(Geo g, Dev d) {
-    const int env = blockIdx.y;
-    if (d.phase[env] != 1) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *sd = reinterpret_cast<uint32_t *>(smem_raw);                       // [Z][Xp]
-    uint8_t *sf = smem_raw + (size_t)g.Z * g.Xp * 4;                              // [Z][Xp]
-    const int y = blockIdx.x, z = threadIdx.y, lane = threadIdx.x;
-    const bool re = d.reinit[env] != 0;
+__device__ __forceinline__ void sweep_xz_row(const Geo &g, const Dev &d, int env, int y, bool re, uint32_t *sd, uint8_t *sf) {
+    const int z = threadIdx.y, lane = threadIdx.x;
+    uint8_t *rowd = d.g_rowd + (size_t)env * g.Y + y;
+    if (!re && d.g_all[env] == 0 && *rowd == 0) return;          // clean row (uniform over the block)
+    __syncthreads();                                             // (also: the previous row's via stage is done with sd/sf)
+    if (z == 0 && lane == 0) *rowd = 0;
+    const uint32_t cap = d.g_cap[env];
+    bool skipped = false;
+    uint32_t gm = 0xFFFFFFFFu;
     const size_t rowoff = (size_t)env * g.cells_p + ((size_t)z * g.Y + y) * g.Xp;
     const int x0 = lane * CPL;
     constexpr int NF = (CPL + 7) / 8;
@@ -167,7 +185,9 @@ __global__ void __launch_bounds__(32 * XR_ZMAX) k_sweep_xz(Geo g, Dev d) {
 #pragma unroll
         for (int i = 0; i < CPL; i++) {
             t = xr_min(t + wx_from_left(g, z, x0 + i, FLG(i)), dd[i]);
-            if (t < dd[i]) { chg |= 1u << i; dd[i] = t; }
+            if (t < dd[i]) {
+                if (t <= cap) { chg |= 1u << i; dd[i] = t; gm = xr_min(gm, t); } else skipped = true;
+            }
         }
     }
     // ---- backward scan
@@ -189,7 +209,9 @@ __global__ void __launch_bounds__(32 * XR_ZMAX) k_sweep_xz(Geo g, Dev d) {
 #pragma unroll
         for (int i = CPL - 1; i >= 0; i--) {
             t = xr_min(t + wx_from_right(g, z, x0 + i, FLG(i)), dd[i]);
-            if (t < dd[i]) { chg |= 1u << i; dd[i] = t; }
+            if (t < dd[i]) {
+                if (t <= cap) { chg |= 1u << i; dd[i] = t; gm = xr_min(gm, t); } else skipped = true;
+            }
         }
     }
     // ---- stage the slice for the via relaxation (bit 7 of the flag byte = "write back")
@@ -204,7 +226,8 @@ __global__ void __launch_bounds__(32 * XR_ZMAX) k_sweep_xz(Geo g, Dev d) {
 #undef FLG
     __syncthreads();
     const int tid = threadIdx.y * 32 + threadIdx.x, nthr = blockDim.y * 32;
-    bool any = false;
+    bool any = false, via_any = false;
+    const int S = g.Xp / 32;
     for (int x = tid; x < g.X; x += nthr) {
         uint32_t v[XR_ZMAX], fz[XR_ZMAX];
 #pragma unroll
@@ -213,22 +236,44 @@ __global__ void __launch_bounds__(32 * XR_ZMAX) k_sweep_xz(Geo g, Dev d) {
 #pragma unroll
         for (int k = 1; k < XR_ZMAX; k++) if (k < g.Z) {
             t = xr_min(t + wgt_v(g, k - 1, k, fz[k]), v[k]);
-            if (t < v[k]) { v[k] = t; fz[k] |= 0x80u; }
+            if (t < v[k]) {
+                if (t <= cap) { v[k] = t; fz[k] |= 0x80u; gm = xr_min(gm, t); via_any = true; } else skipped = true;
+            }
         }
 #pragma unroll
         for (int k = XR_ZMAX - 2; k >= 0; k--) if (k < g.Z - 1) {
             t = xr_min(t + wgt_v(g, k, k, fz[k]), v[k]);
-            if (t < v[k]) { v[k] = t; fz[k] |= 0x80u; }
+            if (t < v[k]) {
+                if (t <= cap) { v[k] = t; fz[k] |= 0x80u; gm = xr_min(gm, t); via_any = true; } else skipped = true;
+            }
         }
 #pragma unroll
         for (int k = 0; k < XR_ZMAX; k++) if (k < g.Z) {
             if (fz[k] & 0x80u) {
                 d.dist[(size_t)env * g.cells_p + ((size_t)k * g.Y + y) * g.Xp + x] = v[k];
+                d.g_slabd[((size_t)env * g.Z + k) * S + (x >> 5)] = 1;          // this column has to be swept along y
                 any = true;
             }
         }
     }
+    if (via_any) *rowd = 1;                                 // a via move lowered a cell: the row is swept again
+    if (skipped) d.g_rowf[(size_t)env * g.Y + y] = 1;
+    gm = __reduce_min_sync(0xFFFFFFFFu, gm);
+    if (lane == 0 && gm != 0xFFFFFFFFu) atomicMin(&d.g_gmin[env], gm);
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 7]), (unsigned long long)g.Z * g.X);
     if (__any_sync(0xFFFFFFFFu, any) && lane == 0) d.changed[env] = 1;
+}
+// grid (ceil(Y / XZ_ROWS), N), block (32, Z)
+template <int CPL>
+__global__ void __launch_bounds__(32 * XR_ZMAX) k_sweep_xz(Geo g, Dev d) {
+    const int env = blockIdx.y;
+    if (d.phase[env] != 1) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *sd = reinterpret_cast<uint32_t *>(smem_raw);                       // [Z][Xp]
+    uint8_t *sf = smem_raw + (size_t)g.Z * g.Xp * 4;                              // [Z][Xp]
+    const bool re = d.reinit[env] != 0;
+    const int y1 = min(g.Y, (int)(blockIdx.x + 1) * XZ_ROWS);
+    for (int y = blockIdx.x * XZ_ROWS; y < y1; y++) sweep_xz_row<CPL>(g, d, env, y, re, sd, sf);
 }
 
 // -------------------------------------------------------------------- sweep y
@@ -240,6 +285,13 @@ __global__ void __launch_bounds__(32 * 16) k_sweep_y(Geo g, Dev d) {
     if (d.phase[env] != 1) return;
     __shared__ uint32_t sW[2][16][32], sD[2][16][32];
     const int z = blockIdx.y, lane = threadIdx.x, w = threadIdx.y, nw = blockDim.y;
+    uint8_t *slabd = d.g_slabd + ((size_t)env * g.Z + z) * (g.Xp / 32) + blockIdx.x;
+    if (d.g_all[env] == 0 && *slabd == 0) return;                // clean slab (uniform over the block)
+    __syncthreads();
+    if (w == 0 && lane == 0) *slabd = 0;
+    const uint32_t cap = d.g_cap[env];
+    bool skipped = false;
+    uint32_t gm = 0xFFFFFFFFu;
     const int x = blockIdx.x * 32 + lane;
     const int y0 = w * TH;
     const bool colok = x < g.X;
@@ -278,7 +330,9 @@ __global__ void __launch_bounds__(32 * 16) k_sweep_y(Geo g, Dev d) {
             uint32_t wv = XR_INF;
             if (y >= 1 && y < g.Y) wv = wgt_y(g, z, g.uniform_y ? (uint32_t)g.dy : (uint32_t)(g.yc[y] - g.yc[y - 1]), f);
             t = xr_min(t + wv, dd[i]);
-            if (t < dd[i]) { chg |= 1ull << i; dd[i] = t; }
+            if (t < dd[i]) {
+                if (t <= cap) { chg |= 1ull << i; dd[i] = t; gm = xr_min(gm, t); } else skipped = true;
+            }
         }
     }
     // backward: entering row y from y+1
@@ -303,14 +357,23 @@ __global__ void __launch_bounds__(32 * 16) k_sweep_y(Geo g, Dev d) {
             uint32_t wv = XR_INF;
             if (y < g.Y - 1) wv = wgt_y(g, z, g.uniform_y ? (uint32_t)g.dy : (uint32_t)(g.yc[y + 1] - g.yc[y]), f);
             t = xr_min(t + wv, dd[i]);
-            if (t < dd[i]) { chg |= 1ull << i; dd[i] = t; }
+            if (t < dd[i]) {
+                if (t <= cap) { chg |= 1ull << i; dd[i] = t; gm = xr_min(gm, t); } else skipped = true;
+            }
         }
     }
     if (colok) {
 #pragma unroll
         for (int i = 0; i < TH; i++)
-            if ((chg >> i) & 1ull) d.dist[base + (size_t)(y0 + i) * g.Xp] = dd[i];
+            if ((chg >> i) & 1ull) {
+                d.dist[base + (size_t)(y0 + i) * g.Xp] = dd[i];
+                d.g_rowd[(size_t)env * g.Y + y0 + i] = 1;                      // this row has to be swept along x
+            }
     }
+    if (skipped) d.g_slabf[((size_t)env * g.Z + z) * (g.Xp / 32) + blockIdx.x] = 1;
+    gm = __reduce_min_sync(0xFFFFFFFFu, gm);
+    if (lane == 0 && gm != 0xFFFFFFFFu) atomicMin(&d.g_gmin[env], gm);
+    if (w == 0 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&d.envstat[8 * (size_t)env + 7]), 32ull * g.Y);
     if (__any_sync(0xFFFFFFFFu, chg != 0ull) && lane == 0) d.changed[env] = 1;
 }
 
@@ -342,26 +405,37 @@ __device__ __forceinline__ void commit_cell(const Geo &g, const Dev &d, int env,
     d.obs[(size_t)env * g.obs_stride + oo] = 1.f;        // channel 0 of the observation, updated in place
     d.cflag[c] |= CF_TREE;
     d.dist[c] = 0;
+    d.g_rowd[(size_t)env * g.Y + y] = 1;                    // full-grid path: the new source's lines are dirty
+    d.g_slabd[((size_t)env * g.Z + z) * (g.Xp / 32) + (x >> 5)] = 1;
 }
 
 // grid N, block 32 (one warp per environment).
 __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
     const int env = blockIdx.x, lane = threadIdx.x;
     if (d.phase[env] != 1) return;
-    if (lane == 0) {                                     // one more pump = 2 full-grid relaxation passes
-        d.envstat[8 * (size_t)env + 2] += 2; d.envstat[8 * (size_t)env + 7] += 2ll * g.cells;
-    }
-    if (d.changed[env] != 0) {                           // not converged yet
-        __syncwarp();
-        if (lane == 0) { d.changed[env] = 0; d.reinit[env] = 0; }
-        return;
-    }
+    if (lane == 0) d.envstat[8 * (size_t)env + 2] += 2;  // one more pump = 2 relaxation passes (over the dirty lines)
     const int net = d.act[2 * env + 1];
     const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
     const int s = ns[net], t = ns[net + 1];
     const size_t aoff = (size_t)env * g.max_aps;
     const size_t eoff = (size_t)env * g.cells_p;
     const bool first = d.first[env] != 0;
+    if (d.changed[env] != 0) {                           // something was written in this pump
+        // bounded stop: once every distance written in a pump is >= the best target distance, all cells below
+        // it are final; otherwise tighten the cap and pump again
+        uint32_t bcur = 0xFFFFFFFFu;
+        for (int i = s + lane; i < t; i += 32)
+            if (!d.ap_conn[aoff + i]) bcur = xr_min(bcur, d.dist[eoff + d.ap_cellp[aoff + i]]);
+        bcur = __reduce_min_sync(0xFFFFFFFFu, bcur);
+        const uint32_t gm = d.g_gmin[env];
+        const bool was_reinit = d.reinit[env] != 0;
+        __syncwarp();
+        if (lane == 0) {
+            d.changed[env] = 0; d.reinit[env] = 0; d.g_all[env] = 0; d.g_gmin[env] = 0xFFFFFFFFu;
+            if (bcur < d.g_cap[env]) d.g_cap[env] = bcur;
+        }
+        if (was_reinit || !(bcur < XR_INF && gm >= bcur)) return;
+    }
     // ---- target = argmin (dist, cell index) over the APs of unconnected pins
     unsigned long long best = ~0ull;
     for (int i = s + lane; i < t; i += 32) {
@@ -491,6 +565,22 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
         left |= (v == 0);
     }
     left = __any_sync(0xFFFFFFFFu, left);
+    if (left && !fail) {
+        // next connection: every deferred line is dirty again; its cap is the best distance the field left by the
+        // previous connections already shows on a target (an upper bound, the tree only grew) -- none after a
+        // re-initialisation, whose field starts from scratch
+        const int S = g.Xp / 32;
+        for (int i = lane; i < g.Y; i += 32)
+            if (d.g_rowf[(size_t)env * g.Y + i]) { d.g_rowf[(size_t)env * g.Y + i] = 0; d.g_rowd[(size_t)env * g.Y + i] = 1; }
+        for (int i = lane; i < g.Z * S; i += 32)
+            if (d.g_slabf[(size_t)env * g.Z * S + i]) { d.g_slabf[(size_t)env * g.Z * S + i] = 0; d.g_slabd[(size_t)env * g.Z * S + i] = 1; }
+        uint32_t b0 = XR_INF;
+        if (!first)
+            for (int i = s + lane; i < t; i += 32)
+                if (!d.ap_conn[aoff + i]) b0 = xr_min(b0, d.dist[eoff + d.ap_cellp[aoff + i]]);
+        b0 = __reduce_min_sync(0xFFFFFFFFu, b0);
+        if (lane == 0) d.g_cap[env] = b0 < XR_INF ? b0 : XR_INF;
+    }
     if (lane == 0) {
         d.wlvia[2 * env] += wl; d.wlvia[2 * env + 1] += via;
         d.path_n[env] = pn;
@@ -505,6 +595,8 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
             d.changed[env] = 1;
             d.reinit[env] = first ? 1 : 0;
             d.first[env] = 0;
+            d.g_all[env] = first ? 1 : 0;                // the re-initialisation pass touches every line
+            d.g_gmin[env] = 0xFFFFFFFFu;
         } else {
             d.phase[env] = 0;
             atomicSub(&d.flags[0], 1);
