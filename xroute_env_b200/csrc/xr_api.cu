@@ -641,19 +641,18 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaSetDevice(env->device);
     // ---- validate against the host mirror of the legal sets (state untouched on error)
-    bool any_route = false, any_act = false;
+    bool any_route = false;
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
         if (a == 0) continue;
         if (!env->h_reset[i]) return fail(env, XR_E_STATE, "step before reset");
-        if (a == -1) { any_act = true; continue; }
+        if (a == -1) continue;
         if (a < 1 || a > g.max_nets || !env->h_has_ap[(size_t)i * (g.max_nets + 1) + a] ||
             env->h_routed[(size_t)i * (g.max_nets + 1) + a] || env->h_done[i]) {
             char buf[128];
             snprintf(buf, sizeof buf, "illegal action %d for environment %d", a, i);
             return fail(env, XR_E_ILLEGAL, buf);
         }
-        any_act = true;
     }
     // p_act / p_lists are reused across calls: the previous step's uploads must have completed
     CK(cudaStreamSynchronize(st)); env->n_sync++;

@@ -353,7 +353,6 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
     constexpr int LC = Log2C<C>::v;
     const int *wd = d.net_win + ((size_t)env * (g.max_nets + 1) + net) * 6;
     const int wx0 = wd[0] & 0xFFFF, wy0 = wd[0] >> 16, WX = wd[1] & 0xFFFF, WY = wd[1] >> 16;
-    const int bx0 = wd[2], bx1 = wd[3], by0 = wd[4], by1 = wd[5];
     Win2Ctx c;
     c.Z = g.Z; c.WX = WX; c.WXp = WX | 1; c.WY = WY; c.WYp = WY | 1; c.rank = rank;
     c.HA = (WY + C - 1) / C; c.WB = (WX + C - 1) / C;
