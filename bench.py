@@ -212,10 +212,30 @@ def ispd_leg(device: int, cpu: bool, n_envs: int = 128, episodes: int = 3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # the single-environment legacy API on the same region: Game.reset/step as train_PPO.py calls them, every
+    # observation copied to a fresh CPU tensor (what the reference's Game returns)
+    from xroute_env_b200 import Game
+    game = Game(geometry=geom, instances=[inst], device=device, max_nets=max(nets), max_aps=len(inst.ap_net))
+    game.reset()
+    for net in orders[:4, 0]:
+        game.step(int(net))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    obs0, _ = game.reset()
+    d2h = obs0.numel() * 4
+    for net in orders[: len(nets), 1]:
+        o, done, *_ = game.step(int(net))
+        d2h += o.numel() * 4
+    wall = time.perf_counter() - t0
+    game._vec.close()
+    legacy = {"value": len(nets) / wall, "unit": "env-steps/s", "ms_per_step": 1e3 * wall / len(nets),
+              "d2h_bytes_per_step": d2h // (len(nets) + 1),
+              "note": "xroute_env_b200.Game (reference-compatible single environment): one episode, observation "
+                      "tensors copied to the host every step"}
     out = {"region": f"{name} (routeBox 39900,79800-79800,119700; {geom.X}x{geom.Y}x{geom.Z}, {len(nets)} nets, "
                      f"{len(inst.ap_net)} access points, {len(inst.block_xyz)} blockages)",
            "envs": n_envs, "value": episodes * len(nets) * n_envs / (ms / 1e3), "unit": "env-steps/s",
-           "ms_per_step": ms / (episodes * len(nets)), "route_paths": vg.route_counters()}
+           "ms_per_step": ms / (episodes * len(nets)), "route_paths": vg.route_counters(), "legacy_game_api": legacy}
     vg.close()
     if cpu:
         import ctypes as C

@@ -70,6 +70,7 @@ class VecGame:
         self._h_done = torch.zeros((self.n_envs,), dtype=torch.uint8, pin_memory=pin)
         self._h_cum = torch.zeros((self.n_envs, _lib.XR_M_COUNT), dtype=torch.int64, pin_memory=pin)
         self._views = {}
+        self._pin_obs = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -203,10 +204,19 @@ class VecGame:
         ch = C.c_int32()
         _lib.check(self._L.xr_obs_channels(self._h, env_id, C.byref(ch)), self._h)
         g = self.geom
-        out = torch.empty((1, ch.value, g.Z, g.Y, g.X), dtype=torch.float32)
-        _lib.check(self._L.xr_obs_copy(self._h, env_id, C.cast(out.data_ptr(), C.POINTER(C.c_float)),
-                                       out.numel(), self._stream()), self._h)
-        return out
+        n = ch.value * g.cells
+        # through a pinned staging buffer (a pageable destination makes the driver stage the copy itself,
+        # several times slower), then one host memcpy into the fresh tensor the caller owns
+        if self._pin_obs is None and torch.cuda.is_available() and self.max_channels * g.cells * 4 <= (2 << 30):
+            self._pin_obs = torch.empty(self.max_channels * g.cells, dtype=torch.float32, pin_memory=True)
+        if self._pin_obs is None:
+            out = torch.empty((1, ch.value, g.Z, g.Y, g.X), dtype=torch.float32)
+            _lib.check(self._L.xr_obs_copy(self._h, env_id, C.cast(out.data_ptr(), C.POINTER(C.c_float)),
+                                           out.numel(), self._stream()), self._h)
+            return out
+        _lib.check(self._L.xr_obs_copy(self._h, env_id, C.cast(self._pin_obs.data_ptr(), C.POINTER(C.c_float)),
+                                       n, self._stream()), self._h)
+        return self._pin_obs[:n].clone().view(1, ch.value, g.Z, g.Y, g.X)
 
     # ------------------------------------------------------------------- host info
     def legal_set(self, env_id: int) -> set[int]:
