@@ -43,6 +43,8 @@ struct XrEnv {
     std::vector<int32_t> h_nrem;
     int32_t *p_act = nullptr;           // pinned [N][2]
     int32_t *p_flags = nullptr;         // pinned [2]
+    unsigned char *p_res = nullptr;     // pinned mirror of the step results: delta int32[N][3], cum int64[N][6], done u8[N]
+    bool res_on_host = false;           // p_res holds the results of the last step (filled with the step's own read-back)
     int32_t *p_ids = nullptr;           // pinned [N]
     uint8_t *p_full = nullptr;          // pinned [N] reset: full observation build needed
     std::vector<uint8_t> h_clean;       // observation buffer of the env satisfies the incremental invariant
@@ -155,6 +157,7 @@ static void xr_free(XrEnv *env) {
     for (void *p : env->allocs) cudaFree(p);
     if (env->p_act) cudaFreeHost(env->p_act);
     if (env->p_flags) cudaFreeHost(env->p_flags);
+    if (env->p_res) cudaFreeHost(env->p_res);
     if (env->p_ids) cudaFreeHost(env->p_ids);
     if (env->p_full) cudaFreeHost(env->p_full);
     if (env->p_lists) cudaFreeHost(env->p_lists);
@@ -273,6 +276,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
 #undef DA
     if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
+        cudaMallocHost(&env->p_res, (sizeof(int32_t) * 3 + sizeof(int64_t) * XR_M_COUNT + 1) * N + 64) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
         cudaMallocHost(&env->p_full, N) != cudaSuccess ||
         cudaMallocHost(&env->p_lists, sizeof(int32_t) * (2 + XR_NB * XR_NG) * N) != cudaSuccess) {
@@ -344,6 +348,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
     if (n_block < 0 || n_ap < 0 || (n_block && !block_xyz) || (n_ap && (!ap_net || !ap_pin || !ap_xyz)))
         return fail(env, XR_E_INVALID, "bad instance arrays");
     cudaSetDevice(env->device);
+    env->res_on_host = false;
     std::vector<uint32_t> ci((size_t)g.cells_p, 0);
     std::vector<uint16_t> an((size_t)g.cells_p, 0);
     for (int z = 0; z < g.Z; z++)
@@ -513,6 +518,7 @@ extern "C" int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *str
     const Geo &g = env->g;
     cudaStream_t st = (cudaStream_t)stream;
     cudaSetDevice(env->device);
+    env->res_on_host = false;
     std::vector<int> ids;
     if (env_ids == nullptr) { ids.resize(g.N); for (int i = 0; i < g.N; i++) ids[i] = i; }
     else {
@@ -765,7 +771,17 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     // ---- environments whose window search escaped, or whose window does not fit on chip,
     // are routed by the full-grid sweeps and finalised in a last pass
     bool need_global = any_global;
+    env->res_on_host = false;
     if (any_route && !need_global) {
+        // the results ride on the same read-back as the flags, so xr_step_results needs no second round trip
+        {
+            int64_t *pc = reinterpret_cast<int64_t *>(env->p_res);
+            int32_t *pd = reinterpret_cast<int32_t *>(pc + (size_t)XR_M_COUNT * g.N);
+            unsigned char *pdone = reinterpret_cast<unsigned char *>(pd + 3 * (size_t)g.N);
+            CK(cudaMemcpyAsync(pc, env->d.cum, sizeof(int64_t) * XR_M_COUNT * g.N, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(pd, env->d.delta, sizeof(int32_t) * 3 * g.N, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(pdone, env->d.done, g.N, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st)); env->n_sync++;
         if (env->p_flags[1] != 0) {
@@ -773,6 +789,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             return fail(env, XR_E_UNROUTABLE, "window maze search failed (inconsistent backtrace)");
         }
         if (env->p_flags[0] > 0) need_global = true;
+        else env->res_on_host = true;
     }
     if (need_global) {
         long long pumps = 0;
@@ -823,6 +840,15 @@ extern "C" int xr_step_results(XrEnv *env, int32_t *delta, uint8_t *done, int64_
     const Geo &g = env->g;
     cudaStream_t st = (cudaStream_t)stream;
     cudaSetDevice(env->device);
+    if (env->res_on_host) {              // already read back by xr_step (nothing ran on the handle since)
+        const int64_t *pc = reinterpret_cast<const int64_t *>(env->p_res);
+        const int32_t *pd = reinterpret_cast<const int32_t *>(pc + (size_t)XR_M_COUNT * g.N);
+        const unsigned char *pdone = reinterpret_cast<const unsigned char *>(pd + 3 * (size_t)g.N);
+        if (delta) memcpy(delta, pd, sizeof(int32_t) * 3 * g.N);
+        if (done) memcpy(done, pdone, g.N);
+        if (cum) memcpy(cum, pc, sizeof(int64_t) * XR_M_COUNT * g.N);
+        return XR_OK;
+    }
     if (delta) CK(cudaMemcpyAsync(delta, env->d.delta, sizeof(int32_t) * 3 * g.N, cudaMemcpyDeviceToHost, st));
     if (done) CK(cudaMemcpyAsync(done, env->d.done, g.N, cudaMemcpyDeviceToHost, st));
     if (cum) CK(cudaMemcpyAsync(cum, env->d.cum, sizeof(int64_t) * XR_M_COUNT * g.N, cudaMemcpyDeviceToHost, st));
