@@ -274,8 +274,19 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly one JSON line: NCCL's start-up banner (printed by the library on its first
+        # communicator when NCCL_DEBUG is set on the box) goes to stderr with everything else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     geom = preset_geometry(PRESET)
     K, W = args.steps, args.warmup
     insts = make_batch(geom, ENVS_PER_GPU, N_NETS, SEED, first_env=rank * ENVS_PER_GPU)
