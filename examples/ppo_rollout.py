@@ -4,10 +4,9 @@
 The batched counterpart of the reference's rollout loop
 (/root/reference/baseline/PPO/train_PPO.py:78-107): observations never leave the GPU -- the
 policy reads the environment's observation block through DLPack (zero copy), scores every
-remaining net with a shared 3-D convolutional tower over its 7-channel block plus the obstacle
-channel (the structure of the reference's RepresentationNetwork,
-baseline/baseline_utils.py:231-379, batched over nets and environments instead of a Python
-loop), samples one legal net per environment, and steps the whole batch.  Only the N chosen
+remaining net with the reference's own RepresentationNetwork (baseline/baseline_utils.py:231-379),
+batched over nets and environments instead of a Python loop (xroute_env_b200/agent.py), samples one
+legal net per environment, and steps the whole batch.  Only the N chosen
 actions (4 bytes each) go to the host and N rewards come back.
 
     python examples/ppo_rollout.py --envs 1024 --steps 64            # one GPU's shard of 8192
@@ -29,34 +28,22 @@ from xroute_env_b200.dist import allreduce_stats, shard_range  # noqa: E402
 
 
 class NetScorer(nn.Module):
-    """Scores each remaining net from (obstacles, its 7 channels); value head on the mean."""
+    """Policy / value heads on the reference's representation network, applied to all (environment, net)
+    blocks at once (xroute_env_b200.agent.BatchedRepresentationNetwork: same parameters as
+    baseline/baseline_utils.py:231-379, so a reference checkpoint can be loaded into ``self.rep``)."""
 
-    def __init__(self, hidden: int = 16):
+    def __init__(self):
         super().__init__()
-        self.tower = nn.Sequential(
-            nn.Conv3d(8, hidden, 3, padding=1), nn.ReLU(),
-            nn.Conv3d(hidden, hidden, 3, stride=2, padding=1), nn.ReLU(),
-            nn.AdaptiveAvgPool3d(1), nn.Flatten())
-        self.pi = nn.Linear(hidden, 1)
-        self.v = nn.Linear(hidden, 1)
+        from xroute_env_b200.agent import BatchedRepresentationNetwork
+        self.rep = BatchedRepresentationNetwork()
+        self.pi = nn.Linear(128, 1)
+        self.v = nn.Linear(64, 1)
 
-    def forward(self, obs: torch.Tensor, n_remaining: torch.Tensor, max_nets: int, chunk: int = 4096):
-        # obs: [N, 2+7*max_nets, Z, Y, X] view of the library-owned buffer (read only)
-        N, _, Z, Y, X = obs.shape
-        nets = obs[:, 2:2 + 7 * max_nets].unflatten(1, (max_nets, 7))            # [N, n, 7, Z, Y, X] (view)
-        valid = torch.arange(max_nets, device=obs.device)[None, :] < n_remaining[:, None]
-        idx = valid.nonzero()                                                     # [M, 2] (env, rank)
-        feats = []
-        for s in range(0, idx.shape[0], chunk):
-            e, r = idx[s:s + chunk, 0], idx[s:s + chunk, 1]
-            x = torch.cat([obs[e, 0:1], nets[e, r]], 1)                          # gather only the live blocks
-            feats.append(self.tower(x))
-        feats = torch.cat(feats) if feats else obs.new_zeros((0, self.pi.in_features))
-        logits = obs.new_full((N, max_nets), float("-inf"))
-        logits[idx[:, 0], idx[:, 1]] = self.pi(feats).squeeze(-1)
-        pooled = obs.new_zeros((N, feats.shape[1])).index_add_(0, idx[:, 0], feats)
-        value = self.v(pooled / n_remaining.clamp(min=1)[:, None].float()).squeeze(-1)
-        return logits, value
+    def forward(self, obs: torch.Tensor, n_remaining: torch.Tensor, max_nets: int):
+        ob, rep, valid = self.rep(obs[:, :2 + 7 * max_nets], n_remaining)       # [N,64], [N,n,64], [N,n]
+        logits = self.pi(torch.cat([rep, ob[:, None, :].expand_as(rep)], -1)).squeeze(-1)
+        logits = logits.masked_fill(~valid, float("-inf"))
+        return logits, self.v(ob).squeeze(-1)
 
 
 def main():
