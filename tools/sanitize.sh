@@ -1,5 +1,7 @@
-# compute-sanitizer memcheck over a small episode through every routing engine (band kernel, dual kernel, full grid)
+# compute-sanitizer over a small episode through every routing engine (band kernel, dual kernel, full grid)
+#   bash tools/sanitize.sh [memcheck|racecheck]
 set -e
+TOOL=${1:-memcheck}
 cat > /tmp/san.py <<'PY'
 import os, sys
 sys.path.insert(0, os.getcwd())
@@ -18,5 +20,5 @@ for kw in (dict(), dict(min_cluster=2), dict(window_margin=-1), dict(window_marg
     print(kw, vg.route_counters(), flush=True)
     vg.close()
 PY
-compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san.py 2>&1 | tail -8
-XR_DUAL_PINS=2 XR_DUAL_MINC=2 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san.py 2>&1 | tail -8
+compute-sanitizer --tool $TOOL --error-exitcode 9 python /tmp/san.py 2>&1 | grep -A1 "Error: Race\|ERROR SUMMARY\|RACECHECK SUMMARY" | cut -c1-260 | sort | uniq -c | sort -rn | head -40
+XR_DUAL_PINS=2 XR_DUAL_MINC=2 compute-sanitizer --tool $TOOL --error-exitcode 9 python /tmp/san.py 2>&1 | grep -A1 "Error: Race\|ERROR SUMMARY\|RACECHECK SUMMARY" | cut -c1-260 | sort | uniq -c | sort -rn | head -40

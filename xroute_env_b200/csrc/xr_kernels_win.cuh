@@ -60,6 +60,7 @@ __device__ __forceinline__ uint32_t win_w(uint32_t lutreg, uint32_t pen, uint32_
 // Collect the set flags of flags[0..n) into c.list (clearing them); returns the count.
 __device__ int win_compact(const WinCtx &c, uint8_t *flags, int n) {
     const int lane = threadIdx.x & 31;
+    __syncthreads();                     // every thread has read the previous count and is done with the previous list
     if (threadIdx.x == 0) *c.cnt = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += WIN_T) {

@@ -58,6 +58,7 @@ template <int C> struct Log2C { static constexpr int v = C == 1 ? 0 : C == 2 ? 1
 
 __device__ int win2_compact(const Win2Ctx &c, uint8_t *flags, int n) {
     const int lane = threadIdx.x & 31;
+    __syncthreads();                     // every thread has read the previous count and is done with the previous list
     if (threadIdx.x == 0) *c.cnt = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += WIN_T) {
