@@ -73,6 +73,14 @@ class ClockSampler:
             self.proc.kill()
         self.f.close()
         sm, mx, reasons = [], 0, set()
+        if os.path.getsize(self.path) == 0:          # the sampler never got a line out: one synchronous query
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=20).stdout
+                with open(self.path, "w") as f:
+                    f.write(out)
+            except Exception:
+                pass
         with open(self.path) as f:
             for line in f:
                 c = [s.strip() for s in line.split(",")]
@@ -326,10 +334,16 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            state["rank_ms"] = [float(v.item()) for v in allt]
+            ms = max(state["rank_ms"])                    # max over ranks
         return ms
 
+    # clocks are sampled from before the warm-up to the end of the timed legs (the timed region alone can be
+    # shorter than nvidia-smi's start-up when eight ranks share the host)
+    sampler = ClockSampler(local)
+    sampler.start()
     # warm-up (untimed)
     for _ in range(W):
         one_step(False)
@@ -338,15 +352,14 @@ def run_ours(args):
         one_step(False)
     base_t = state["t"]
 
-    sampler = ClockSampler(local)
     c0 = vg.counters()
-    sampler.start()
     ms_dev = timed(K, read_results=False)
-    clocks = sampler.stop()
+    rank_ms = [round(v / K, 4) for v in state.get("rank_ms", [ms_dev])]
     c1 = vg.counters()
     while state["t"] % N_NETS != 0:
         one_step(False)
     ms_e2e = timed(K, read_results=True)
+    clocks = sampler.stop()
     while state["t"] % N_NETS != 0:
         one_step(False)
     # profiled leg: per-kernel-class CUDA-event timing on the launching stream
@@ -477,7 +490,7 @@ def run_ours(args):
         d2h = ENVS_PER_GPU * (3 * 4 + 1 + 6 * 8)
         line = {
             "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms_dev / K, "ms_per_step_by_rank": rank_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"SYN-256 256x256x9 grid, {ENVS_PER_GPU} envs/GPU, {N_NETS} nets/env, random net "
                                    "order, back-to-back episodes (reset every 32 steps); obs+route+reward per env-step",
