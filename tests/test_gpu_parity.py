@@ -330,3 +330,44 @@ def test_real_ispd18_test1_regions(name):
     g, inst = load_regions(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
                                         "ispd18_test1_regions.npz"))[name]
     _run_episode(g, [inst, inst], seed=17, check_obs_every=5)
+
+
+def test_stop_idle_single_pin_and_state_errors():
+    """Protocol edge cases of net_ordering.proto: -1 stops an environment (:48), 0 leaves it untouched, a net with
+    a single pin is only marked routed (nothing to connect), stepping before the first reset is an error."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    from xroute_env_b200._lib import XrError
+    from xroute_env_b200.instances import Instance
+    geom = ispd18_geometry(16, 14, 4)
+    inst = Instance(block_xyz=np.array([[5, 5, 0], [6, 5, 0]], np.int32),
+                    ap_net=np.array([1, 1, 2, 2, 3, 3, 3], np.int32), ap_pin=np.array([1, 1, 1, 2, 1, 2, 3], np.int32),
+                    ap_xyz=np.array([[2, 2, 0], [3, 2, 0], [1, 8, 0], [12, 9, 1], [4, 11, 0], [9, 3, 1], [13, 12, 0]], np.int32))
+    vg = VecGame(geom, [inst, inst, inst], device=0)
+    with pytest.raises(XrError):
+        vg.step(np.array([1, 1, 1], np.int32))                      # before reset
+    vg.reset()
+    orc = [OracleEnv(geom, inst) for _ in range(3)]
+    obs1_before = vg.obs_host(1).clone()
+    vg.step(np.array([1, 0, -1], np.int32))                         # single-pin net | idle | stop
+    delta, done, cum = vg.results_host()
+    m = orc[0].step(1)
+    assert [int(v) for v in delta[0]] == [m["d_violation"], m["d_wirelength"], m["d_via"]] == [0, 0, 0]
+    assert vg.legal_set(0) == {2, 3} == set(orc[0].remaining()) and not int(done[0])
+    assert np.array_equal(vg.obs_host(0).numpy(), orc[0].obs())
+    assert [int(v) for v in delta[1]] == [0, 0, 0] and vg.legal_set(1) == {1, 2, 3} and not int(done[1])
+    assert np.array_equal(vg.obs_host(1).numpy(), obs1_before.numpy())
+    assert int(done[2]) == 1 and [int(v) for v in delta[2]] == [0, 0, 0]
+    with pytest.raises(XrError):
+        vg.step(np.array([0, 0, 2], np.int32))                      # environment 2 is stopped
+    vg.step(np.array([3, 2, 0], np.int32))
+    delta, done, cum = vg.results_host()
+    for e, net in ((0, 3), (1, 2)):
+        m = orc[e].step(net)
+        assert [int(v) for v in cum[e]][:3] == [m["violation"], m["wirelength"], m["via"]]
+        oc, oo, ocost = orc[e].last_paths(); gc, go, gcost = vg.paths(e)
+        assert np.array_equal(oc, gc) and np.array_equal(ocost, gcost)
+        assert np.array_equal(vg.obs_host(e).numpy(), orc[e].obs())
+    vg.reset([2])
+    assert vg.legal_set(2) == {1, 2, 3} and not int(vg.done.cpu()[2])
+    vg.close()
