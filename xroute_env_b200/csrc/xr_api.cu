@@ -724,13 +724,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * 2 * g.N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(env->d.mode, modes, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(env->d.grp, grps, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
-    if (any_route) {
+    if (any_route)
         CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * XR_NB * XR_NG * g.N, cudaMemcpyHostToDevice, st));
-        Launch L(env, XR_K_ROUTE_BEGIN, st);
-        k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d);
-    }
-    { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
-    CK(cudaGetLastError());
     // ---- the two post-route groups run on their own streams: the light group's metric and
     // observation kernels (HBM bound) overlap the heavy group's on-chip routing
     int maxn_grp[XR_NG] = {};
@@ -742,6 +737,14 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     int n_nonempty = 0;
     for (int k = 0; k < XR_NG; k++) n_nonempty += n_grp[k] > 0;
     const bool split = n_nonempty > 1 && any_route;
+    // route prologue (freeze the cost flags, clear the distance field, seed the sources): once for everybody, or --
+    // when the groups run on their own streams -- per group, so that the heavy group, the long pole of the step,
+    // starts routing as soon as its own few environments are ready
+    if (!split) {
+        if (any_route) { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1); }
+        { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d, -1); }
+        CK(cudaGetLastError());
+    }
     if (split) CK(cudaEventRecord(env->ev_fork, st));
     for (int gi = 0; gi < XR_NG; gi++) {
         const int grp = XR_NG - 1 - gi;                   // heaviest group first: it is the long pole
@@ -749,7 +752,11 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         if (!has && grp != 0) continue;                   // (group 0 always runs: it also finalises idle envs)
         cudaStream_t sg = split ? env->gs[grp] : st;
         env->cur_grp = grp;
-        if (split) CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
+        if (split) {
+            CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
+            if (has) { Launch L(env, XR_K_ROUTE_BEGIN, sg); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
+            { Launch L(env, XR_K_MISC, sg); k_seed<<<g.N, 64, 0, sg>>>(env->g, env->d, grp); }
+        }
         for (int b = XR_NB - 1; b >= 0; b--) {              // widest clusters first: they need a whole GPC
             if (!nb[grp][b]) continue;
             int rc = launch_route_win(env, sg, CS[b], b >= NB_BAND, nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);

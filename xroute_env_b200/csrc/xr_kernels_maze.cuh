@@ -30,10 +30,10 @@
 // ---------------------------------------------------------------- route begin
 // Freeze the per-cell cost flags of the net each environment routes this step
 // and clear its distance field.  4 cells per thread, 16-byte stores.
-__global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d) {
+__global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp) {
     const int env = blockIdx.y;
     const int net = d.act[2 * env + 1];
-    if (net == 0) return;
+    if (net == 0 || (grp >= 0 && d.grp[env] != grp)) return;  // grp >= 0: only this post-route group's environments
     const size_t eoff = (size_t)env * g.cells_p;
     const int n4 = g.cells_p >> 2;
     const uint4 *ci4 = reinterpret_cast<const uint4 *>(d.cellinfo + eoff);
@@ -61,8 +61,9 @@ __global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d) {
 
 // Per-environment step prologue: mark the chosen net routed, arm the route state
 // machine and seed the sources (all APs of the static source pin).
-__global__ void k_seed(Geo g, Dev d) {
+__global__ void k_seed(Geo g, Dev d, int grp) {
     const int env = blockIdx.x;
+    if (grp >= 0 && d.grp[env] != grp) return;
     const int raw = d.act[2 * env], net = d.act[2 * env + 1];
     if (threadIdx.x == 0) {
         d.obs_do[env] = (raw != 0);
