@@ -45,6 +45,7 @@ struct XrEnv {
     int32_t *p_flags = nullptr;         // pinned [2]
     unsigned char *p_res = nullptr;     // pinned mirror of the step results: delta int32[N][3], cum int64[N][6], done u8[N]
     bool res_on_host = false;           // p_res holds the results of the last step (filled with the step's own read-back)
+    size_t rb_bytes = 0;                // size of the device read-back block (cum | delta | flags | done)
     int32_t *p_ids = nullptr;           // pinned [N]
     uint8_t *p_full = nullptr;          // pinned [N] reset: full observation build needed
     std::vector<uint8_t> h_clean;       // observation buffer of the env satisfies the incremental invariant
@@ -160,7 +161,7 @@ static void xr_free(XrEnv *env) {
     if (env->p_res) cudaFreeHost(env->p_res);
     if (env->p_ids) cudaFreeHost(env->p_ids);
     if (env->p_full) cudaFreeHost(env->p_full);
-    if (env->p_lists) cudaFreeHost(env->p_lists);
+
     for (int k = 0; k < XR_NG; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
     for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -250,16 +251,30 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.obst_obs, N * g.cells_o); DA(d.routed, N * (g.max_nets + 1)); DA(d.legal, N * (g.max_nets + 1));
     DA(d.rank_net, N * g.max_nets); DA(d.n_remaining, N);
     DA(d.dist, N * g.cells_p); DA(d.cflag, N * g.cells_p);
-    DA(d.act, N * 2); DA(d.phase, N); DA(d.changed, N); DA(d.reinit, N); DA(d.first, N);
-    DA(d.ap_conn, N * g.max_aps); DA(d.flags, 4);
+    DA(d.phase, N); DA(d.changed, N); DA(d.reinit, N); DA(d.first, N);
+    {   // everything a step uploads lives in one block (one H2D copy): act [N][2] | mode [N] | grp [N] | env lists
+        int32_t *up;
+        DA(up, N * (4 + XR_NB * XR_NG));
+        d.act = up; d.mode = up + 2 * N; d.grp = up + 3 * N; env->d_lists = up + 4 * N;
+    }
+    {   // ... and everything a step reads back in another (one D2H copy): cum i64 [N][6] | delta i32 [N][3] | flags i32 [4] | done u8 [N]
+        int64_t *rb;
+        DA(rb, N * XR_M_COUNT + (N * 3 + 4 + 1) / 2 + (N + 7) / 8 + 1);
+        d.cum = reinterpret_cast<long long *>(rb);
+        d.delta = reinterpret_cast<int32_t *>(rb + N * XR_M_COUNT);
+        d.flags = d.delta + 3 * N;
+        d.done = reinterpret_cast<uint8_t *>(d.flags + 4);
+        env->rb_bytes = sizeof(int64_t) * N * XR_M_COUNT + sizeof(int32_t) * (3 * N + 4) + N;
+    }
+    DA(d.ap_conn, N * g.max_aps);
     DA(d.g_rowd, N * g.Y); DA(d.g_rowf, N * g.Y); DA(d.g_slabd, N * g.Z * (g.Xp / 32)); DA(d.g_slabf, N * g.Z * (g.Xp / 32));
     DA(d.g_cap, N); DA(d.g_gmin, N); DA(d.g_all, N);
-    DA(d.msum, N * 4); DA(d.delta, N * 3); DA(d.cum, N * 6); DA(d.wlvia, N * 2); DA(d.done, N);
+    DA(d.msum, N * 4); DA(d.wlvia, N * 2);
     DA(d.reward, N); DA(d.envstat, N * 8); DA(d.stats, XR_STATS_COUNT); DA(d.obs_do, N); DA(d.obs_full, N);
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.mode, N); DA(d.grp, N); DA(d.fin, N); DA(env->d_lists, N * XR_NB * XR_NG); DA(d.dbg, 16); DA(d.netfeat, N * (g.max_nets + 1) * XR_NF);
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.fin, N); DA(d.dbg, 16); DA(d.netfeat, N * (g.max_nets + 1) * XR_NF);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -274,15 +289,15 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         d.obs = reinterpret_cast<float *>(q);
     }
 #undef DA
-    if (cudaMallocHost(&env->p_act, sizeof(int32_t) * 2 * N) != cudaSuccess ||
+    if (cudaMallocHost(&env->p_act, sizeof(int32_t) * (4 + XR_NB * XR_NG) * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaMallocHost(&env->p_res, (sizeof(int32_t) * 3 + sizeof(int64_t) * XR_M_COUNT + 1) * N + 64) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
-        cudaMallocHost(&env->p_full, N) != cudaSuccess ||
-        cudaMallocHost(&env->p_lists, sizeof(int32_t) * (2 + XR_NB * XR_NG) * N) != cudaSuccess) {
+        cudaMallocHost(&env->p_full, N) != cudaSuccess) {
         xr_free(env);
         return fail(nullptr, XR_E_CUDA, "cudaMallocHost failed");
     }
+    env->p_lists = env->p_act + 2 * N;                  // one pinned block, same order as the device block: act | mode | grp | lists
     env->h_routed.assign(N * (g.max_nets + 1), 0);
     env->h_has_ap.assign(N * (g.max_nets + 1), 0);
     env->h_npins.assign(N * (g.max_nets + 1), 0);
@@ -721,11 +736,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
         modes[i] = mode; grps[i] = grp;
     }
-    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * 2 * g.N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(env->d.mode, modes, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(env->d.grp, grps, sizeof(int32_t) * g.N, cudaMemcpyHostToDevice, st));
-    if (any_route)
-        CK(cudaMemcpyAsync(env->d_lists, env->p_lists + 2 * g.N, sizeof(int32_t) * XR_NB * XR_NG * g.N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * (size_t)(any_route ? 4 + XR_NB * XR_NG : 4) * g.N,
+                       cudaMemcpyHostToDevice, st));       // act | mode | grp | env lists in one copy
     // ---- the two post-route groups run on their own streams: the light group's metric and
     // observation kernels (HBM bound) overlap the heavy group's on-chip routing
     int maxn_grp[XR_NG] = {};
@@ -781,16 +793,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     env->res_on_host = false;
     if (any_route && !need_global) {
         // the results ride on the same read-back as the flags, so xr_step_results needs no second round trip
-        {
-            int64_t *pc = reinterpret_cast<int64_t *>(env->p_res);
-            int32_t *pd = reinterpret_cast<int32_t *>(pc + (size_t)XR_M_COUNT * g.N);
-            unsigned char *pdone = reinterpret_cast<unsigned char *>(pd + 3 * (size_t)g.N);
-            CK(cudaMemcpyAsync(pc, env->d.cum, sizeof(int64_t) * XR_M_COUNT * g.N, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(pd, env->d.delta, sizeof(int32_t) * 3 * g.N, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(pdone, env->d.done, g.N, cudaMemcpyDeviceToHost, st));
-        }
-        CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(env->p_res, env->d.cum, env->rb_bytes, cudaMemcpyDeviceToHost, st));   // cum | delta | flags | done
         CK(cudaStreamSynchronize(st)); env->n_sync++;
+        memcpy(env->p_flags, env->p_res + sizeof(int64_t) * XR_M_COUNT * g.N + sizeof(int32_t) * 3 * g.N, sizeof(int32_t) * 2);
         if (env->p_flags[1] != 0) {
             cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
             return fail(env, XR_E_UNROUTABLE, "window maze search failed (inconsistent backtrace)");
@@ -850,7 +855,7 @@ extern "C" int xr_step_results(XrEnv *env, int32_t *delta, uint8_t *done, int64_
     if (env->res_on_host) {              // already read back by xr_step (nothing ran on the handle since)
         const int64_t *pc = reinterpret_cast<const int64_t *>(env->p_res);
         const int32_t *pd = reinterpret_cast<const int32_t *>(pc + (size_t)XR_M_COUNT * g.N);
-        const unsigned char *pdone = reinterpret_cast<const unsigned char *>(pd + 3 * (size_t)g.N);
+        const unsigned char *pdone = reinterpret_cast<const unsigned char *>(pd + 3 * (size_t)g.N + 4);
         if (delta) memcpy(delta, pd, sizeof(int32_t) * 3 * g.N);
         if (done) memcpy(done, pdone, g.N);
         if (cum) memcpy(cum, pc, sizeof(int64_t) * XR_M_COUNT * g.N);
