@@ -319,7 +319,7 @@ def run_ours(args):
         vg.step(sched_p[t])
         state["t"] = t + 1
         if read_results:
-            delta, done, cum = vg.results_host()
+            delta, done, cum = vg.results_host_np()
             return float(-(500.0 * delta[:, 0].sum() + 4.0 * delta[:, 2].sum() + 0.5 * delta[:, 1].sum()))
         return None
 

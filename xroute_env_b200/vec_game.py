@@ -71,6 +71,7 @@ class VecGame:
         self._h_cum = torch.zeros((self.n_envs, _lib.XR_M_COUNT), dtype=torch.int64, pin_memory=pin)
         self._views = {}
         self._pin_obs = None
+        self._h_np = (self._h_delta.numpy(), self._h_done.numpy(), self._h_cum.numpy())   # same pinned memory
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -124,6 +125,11 @@ class VecGame:
             C.cast(self._h_done.data_ptr(), C.POINTER(C.c_uint8)),
             C.cast(self._h_cum.data_ptr(), C.POINTER(C.c_int64)), self._stream()), self._h)
         return self._h_delta, self._h_done, self._h_cum
+
+    def results_host_np(self):
+        """``results_host`` as numpy views of the same pinned buffers (no tensor-op overhead on the host)."""
+        self.results_host()
+        return self._h_np
 
     # -------------------------------------------------------------- zero-copy views
     def _buffer(self, which: int) -> torch.Tensor:
