@@ -218,7 +218,7 @@ __device__ uint32_t win_sweep_y(const WinCtx &c, int n, long long &work) {
 
 // one thread per dirty (z, ly) row of the band
 #ifndef WIN_COOP_X_LINES
-#define WIN_COOP_X_LINES 512         // at most this many dirty rows ...
+#define WIN_COOP_X_LINES 128         // at most this many dirty rows (measured: 96-192 best on T1-7x7 and SYN-256) ...
 #endif
 #ifndef WIN_COOP_X_LEN
 #define WIN_COOP_X_LEN 64            // ... of at least this many cells: lanes cooperate on each row
