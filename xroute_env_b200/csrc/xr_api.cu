@@ -716,7 +716,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
                     if (bytes <= env->smem_cap) bucket = b;
                 }
             }
-            if (WX > 0 && bucket < 0) {
+            if (WX > 0 && bucket < 0 && WX < 1024 && WY < 1024 &&          // (the window kernels cache the net's access
+                env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= WIN_TGT_CAP) {   //  points on chip, packed 10+10+12 bits)
                 for (int b = 0; b < NB_BAND && bucket < 0; b++) {
                     if (CS[b] < mc) continue;
                     const int H = (WY + CS[b] - 1) / CS[b];

@@ -34,7 +34,7 @@ namespace cg = cooperative_groups;
 #define WIN_TGT_CAP 256
 // words of shared memory besides the cells: tables, target list, dirty flags, work list
 #define WIN_AUX_WORDS(Z, H, WX)                                                                   \
-    (3 * (Z) + 3 * (Z) + 24 * (Z) + (WX) + 2 + (H) + 4 + 64 + 2 * WIN_TGT_CAP +                                \
+    (3 * (Z) + 3 * (Z) + 24 * (Z) + (WX) + 2 + (H) + 4 + 64 + 5 * WIN_TGT_CAP +                                \
      ((Z) * (H) + (Z) * (WX) + (H) * (WX)) / 4 + 3 + ((Z) * ((H) > (WX) ? (H) : (WX))) / 2 + 2 + WIN_TGT_CAP + 8)
 
 struct WinCtx {
@@ -326,7 +326,6 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     const int tid = threadIdx.x, lane = tid & 31;
     const int *wd = d.net_win + ((size_t)env * (g.max_nets + 1) + net) * 6;
     const int wx0 = wd[0] & 0xFFFF, wy0 = wd[0] >> 16, WX = wd[1] & 0xFFFF, WY = wd[1] >> 16;
-    const int bx0 = wd[2], bx1 = wd[3], by0 = wd[4], by1 = wd[5];      // DBU bbox of the net's APs
     const int H = (WY + C - 1) / C;
     WinCtx c;
     c.Z = g.Z; c.WX = WX; c.WXp = WX | 1; c.HH = H + 2; c.H = H;
@@ -347,6 +346,12 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     int *s_tgt = reinterpret_cast<int *>(aux); aux += 2 * WIN_TGT_CAP;   // DBU coordinates of the unconnected APs
     uint32_t *s_tloc = aux; aux += WIN_TGT_CAP;             // cell index of the unconnected APs inside this band
     uint32_t *s_red = aux; aux += 8;                        // [parity][0] smallest distance written, [1] best target in band, [4] #local targets
+    // the net's access points, cached on chip (the host sends a net here only if it has at most WIN_TGT_CAP of them)
+    uint32_t *s_apc = aux; aux += WIN_TGT_CAP;              // window cell: lx | wy << 10 | z << 20
+    uint16_t *s_appin = reinterpret_cast<uint16_t *>(aux); aux += WIN_TGT_CAP / 2;
+    uint16_t *s_tidx = reinterpret_cast<uint16_t *>(aux); aux += WIN_TGT_CAP / 2;    // unconnected access points
+    uint8_t *s_apconn = reinterpret_cast<uint8_t *>(aux); aux += WIN_TGT_CAP / 4;
+    uint8_t *s_apon = reinterpret_cast<uint8_t *>(aux); aux += WIN_TGT_CAP / 4;
     c.cnt = &s_flag[5];
 #ifdef WIN_PHASE_CRIT
     uint32_t *s_ph = aux; aux += 8;                         // this rank's phase times of the iteration (diagnostics)
@@ -395,14 +400,19 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
     __syncthreads();
     // ---- seeds: access points of the source pin inside this band
     const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
-    const int s = ns[net], t = ns[net + 1];
-    const size_t aoff = (size_t)env * g.max_aps;
+    const int s = ns[net], t = ns[net + 1], n_ap = t - s;
+    const size_t aoff = (size_t)env * g.max_aps + s;
     const unsigned srcpin = d.net_srcpin[(size_t)env * (g.max_nets + 1) + net];
-    for (int i = s + tid; i < t; i += WIN_T) {
-        if (d.ap_pin[aoff + i] != srcpin) continue;
-        atomicAdd(&s_flag[6], 1);                        // every CTA counts all source APs
+    for (int i = tid; i < n_ap; i += WIN_T) {
         const int cp = d.ap_cellp[aoff + i];
         const int x = cp % g.Xp - wx0, wy = (cp / g.Xp) % g.Y - wy0, z = cp / (g.Xp * g.Y);
+        const unsigned pin = d.ap_pin[aoff + i];
+        s_apc[i] = (uint32_t)(x | (wy << 10) | (z << 20));
+        s_tgt[2 * i] = g.xc[wx0 + x]; s_tgt[2 * i + 1] = g.yc[wy0 + wy];       // DBU position (exit-test heuristic)
+        s_appin[i] = (uint16_t)pin;
+        s_apconn[i] = pin == srcpin;
+        if (pin != srcpin) continue;
+        atomicAdd(&s_flag[6], 1);                        // every CTA counts all source APs
         const int ly = wy - c.ry0 + 1;
         if (ly >= 1 && ly <= c.h) {
             c.cell[((size_t)z * c.HH + ly) * c.WXp + x] &= ~WMASK;
@@ -431,22 +441,19 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         // the DBU coordinates (exit-test heuristic); each keeps the cells inside its band.
         if (tid == 0) { s_flag[4] = 0; s_red[4] = 0; }
         __syncthreads();
-        for (int i = s + tid; i < t; i += WIN_T) {
-            if (d.ap_conn[aoff + i]) continue;
-            const int cp = d.ap_cellp[aoff + i];
-            const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
-            const int k = atomicAdd(&s_flag[4], 1);
-            if (k < WIN_TGT_CAP) { s_tgt[2 * k] = g.xc[gx]; s_tgt[2 * k + 1] = g.yc[gy]; }
-            const int ly = gy - wy0 - c.ry0 + 1;
-            if (ly >= 1 && ly <= c.h) {
-                const unsigned m = atomicAdd(&s_red[4], 1u);
-                if (m < WIN_TGT_CAP) s_tloc[m] = (uint32_t)(((size_t)z * c.HH + ly) * c.WXp + (gx - wx0));
-            }
+        for (int i = tid; i < n_ap; i += WIN_T) {
+            if (s_apconn[i]) continue;
+            const uint32_t pc = s_apc[i];
+            const int x = pc & 1023, wy = (pc >> 10) & 1023, z = pc >> 20;
+            s_tidx[atomicAdd(&s_flag[4], 1)] = (uint16_t)i;
+            const int ly = wy - c.ry0 + 1;
+            if (ly >= 1 && ly <= c.h)
+                s_tloc[atomicAdd(&s_red[4], 1u)] = (uint32_t)(((size_t)z * c.HH + ly) * c.WXp + x);
         }
         __syncthreads();
         const int n_tgt = s_flag[4];
         const int n_loc = (int)s_red[4];
-        const bool early = n_tgt <= WIN_TGT_CAP;          // bounded stop needs the complete target list
+        const bool early = true;                          // the target list is always complete (n_ap <= WIN_TGT_CAP)
         // ---- relax until nothing below the best target distance can change any more.
         // A sweep only ever writes values >= the value it propagates from, so once every
         // distance written in an iteration is >= B (the best target distance), all cells
@@ -557,14 +564,14 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         if (tid == 0) s_best[0] = ~0ull;
         __syncthreads();
         unsigned long long best = ~0ull;
-        for (int i = s + tid; i < t; i += WIN_T) {
-            if (d.ap_conn[aoff + i]) continue;
-            const int cp = d.ap_cellp[aoff + i];
-            const int gx = cp % g.Xp, gy = (cp / g.Xp) % g.Y, z = cp / (g.Xp * g.Y);
-            const int x = gx - wx0, ly = gy - wy0 - c.ry0 + 1;
+        for (int k = tid; k < n_tgt; k += WIN_T) {
+            const uint32_t pc = s_apc[s_tidx[k]];
+            const int x = pc & 1023, wy = (pc >> 10) & 1023, z = pc >> 20;
+            const int ly = wy - c.ry0 + 1;
             if (ly < 1 || ly > c.h) continue;
             const uint32_t dv = c.cell[((size_t)z * c.HH + ly) * c.WXp + x] & WMASK;
-            const unsigned long long key = ((unsigned long long)dv << 32) | (unsigned)cp;
+            const unsigned cp = (unsigned)((z * g.Y + wy0 + wy) * g.Xp + wx0 + x);
+            const unsigned long long key = ((unsigned long long)dv << 32) | cp;
             best = key < best ? key : best;
         }
 #pragma unroll
@@ -602,17 +609,11 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                 const int px = g.xc[wx0 + x], py = g.yc[wy0 + c.ry0 + ly - 1];
                 // admissible remaining cost: L1 track distance (>= 1 cost unit per DBU) to the
                 // nearest unconnected access point; bounding box of all APs if the list overflowed
-                uint32_t hmin;
-                if (n_tgt <= WIN_TGT_CAP) {
-                    hmin = 0xFFFFFFFFu;
-                    for (int j = 0; j < n_tgt; j++) {
-                        const uint32_t hh = (uint32_t)(abs(px - s_tgt[2 * j]) + abs(py - s_tgt[2 * j + 1]));
-                        hmin = hh < hmin ? hh : hmin;
-                    }
-                } else {
-                    const uint32_t hx = px < bx0 ? bx0 - px : (px > bx1 ? px - bx1 : 0);
-                    const uint32_t hy = py < by0 ? by0 - py : (py > by1 ? py - by1 : 0);
-                    hmin = hx + hy;
+                uint32_t hmin = 0xFFFFFFFFu;
+                for (int j = 0; j < n_tgt; j++) {
+                    const int a = s_tidx[j];
+                    const uint32_t hh = (uint32_t)(abs(px - s_tgt[2 * a]) + abs(py - s_tgt[2 * a + 1]));
+                    hmin = hh < hmin ? hh : hmin;
                 }
                 if (dv + hmin <= B) esc = true;
             }
@@ -651,6 +652,19 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
             auto inwin = [&](int x, int y, int z) {
                 return x >= wx0 && x < wx0 + WX && y >= wy0 && y < wy0 + WY && z >= 0 && z < g.Z;
             };
+            // The walk only touches the on-chip cells and the path list; the global state of the new path cells
+            // (occupancy, observation bytes, tree flags) is committed from a pending list (s_tloc is free here) in
+            // parallel passes instead of one global round trip per straight run.
+            int pend = 0;
+            auto flush = [&]() {
+                __syncwarp();
+                for (int k = lane; k < pend; k += 32) {
+                    const uint32_t q = s_tloc[k];
+                    commit_cell(g, d, env, net, wx0 + (int)(q & 1023u), wy0 + (int)((q >> 10) & 1023u), (int)(q >> 20));
+                }
+                __syncwarp();
+                pend = 0;
+            };
             for (;;) {
                 __syncwarp();
                 uint32_t *pc = win_cell_ptr<C>(cluster, c, H, cx - wx0, cy - wy0, cz);
@@ -672,8 +686,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                     const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                     const int run = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
                     if (run > 0) {
+                        if (pend + 32 > WIN_TGT_CAP) flush();
                         if (lane < run) {
-                            commit_cell(g, d, env, net, ax, ay, az);
+                            s_tloc[pend + lane] = (uint32_t)((ax - wx0) | ((ay - wy0) << 10) | (az << 20));
                             *pa = (*pa & ~WMASK) | (CF_TREE << 28);
                             win_mark<C>(cluster, c, ax - wx0, ay - wy0, az);
                             if (pn + lane < g.path_cap) path[pn + lane] = (az * g.Y + ay) * g.X + ax;
@@ -681,7 +696,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                             else if (last < 2) wl += abs(g.xc[ax] - g.xc[bx]);
                             else wl += abs(g.yc[ay] - g.yc[by]);
                         }
-                        pn += run;
+                        pn += run; pend += run;
                         cx -= run * ddx; cy -= run * ddy; cz -= run * ddz;
                         continue;
                     }
@@ -699,8 +714,9 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                 if (m == 0u) { fail = true; break; }
                 const int dir = __ffs(m) - 1;
+                if (pend + 1 > WIN_TGT_CAP) flush();
                 if (lane == dir) {
-                    commit_cell(g, d, env, net, cx, cy, cz);
+                    s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
                     *pc = (vc & ~WMASK) | (CF_TREE << 28);
                     win_mark<C>(cluster, c, cx - wx0, cy - wy0, cz);
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
@@ -708,16 +724,17 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                     else if (dir < 2) wl += abs(g.xc[cx] - g.xc[px]);
                     else wl += abs(g.yc[cy] - g.yc[py]);
                 }
-                pn += 1;
+                pn += 1; pend += 1;
                 cx = __shfl_sync(0xFFFFFFFFu, px, dir);
                 cy = __shfl_sync(0xFFFFFFFFu, py, dir);
                 cz = __shfl_sync(0xFFFFFFFFu, pz, dir);
                 last = dir;
             }
             if (!fail) {
+                if (first && pend + 1 > WIN_TGT_CAP) flush();
                 if (lane == 0) {
                     if (first) {
-                        commit_cell(g, d, env, net, cx, cy, cz);
+                        s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
                         uint32_t *pc = win_cell_ptr<C>(cluster, c, H, cx - wx0, cy - wy0, cz);
                         *pc = (*pc & ~WMASK) | (CF_TREE << 28);
                         win_mark<C>(cluster, c, cx - wx0, cy - wy0, cz);
@@ -725,33 +742,14 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                 }
                 pn += 1;
+                if (first) pend += 1;
             }
+            flush();
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 wl += __shfl_xor_sync(0xFFFFFFFFu, wl, off);
                 via += __shfl_xor_sync(0xFFFFFFFFu, via, off);
             }
-            __syncwarp();
-            // pin bookkeeping on the global TREE marks written by commit_cell
-            __threadfence_block();
-            for (int i = s + lane; i < t; i += 32) {
-                if (d.ap_conn[aoff + i]) continue;
-                const unsigned pin = d.ap_pin[aoff + i];
-                bool on = false;
-                for (int j = i; j >= s && d.ap_pin[aoff + j] == pin && !on; j--)
-                    on = (d.cflag[eoff + d.ap_cellp[aoff + j]] & CF_TREE) != 0;
-                for (int j = i + 1; j < t && d.ap_pin[aoff + j] == pin && !on; j++)
-                    on = (d.cflag[eoff + d.ap_cellp[aoff + j]] & CF_TREE) != 0;
-                if (on) d.ap_conn[aoff + i] = 2;
-            }
-            __syncwarp();
-            bool left = false;
-            for (int i = s + lane; i < t; i += 32) {
-                uint8_t v = d.ap_conn[aoff + i];
-                if (v == 2) { d.ap_conn[aoff + i] = 1; v = 1; }
-                left |= (v == 0);
-            }
-            left = __any_sync(0xFFFFFFFFu, left);
             if (lane == 0) {
                 d.wlvia[2 * env] += wl; d.wlvia[2 * env + 1] += via;
                 d.path_n[env] = pn;
@@ -762,15 +760,32 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
                 d.conn_n[env] = cn + 1;
                 d.envstat[8 * (size_t)env + 3] += 1;
                 if (fail) d.flags[1] = 3;
-                s_flag[3] = (left && !fail) ? 1 : 0;
-                __threadfence();
+                s_flag[3] = fail ? 0 : 1;
             }
         }
         if (C > 1) cluster.sync(); else __syncthreads();
+        const int go_on = (C > 1) ? *cluster.map_shared_rank(&s_flag[3], 0) : s_flag[3];
+        // ---- pin bookkeeping, by every CTA on its own copy: a pin is connected once any of its access points is on
+        // the tree (tree bit of the on-chip cell); rank 0 mirrors the flags to global memory for a hand-over
+        for (int i = tid; i < n_ap; i += WIN_T) {
+            const uint32_t q = s_apc[i];
+            s_apon[i] = s_apconn[i] ? 1 : (((*win_cell_ptr<C>(cluster, c, H, q & 1023, (q >> 10) & 1023, q >> 20)) >> 31) & 1u);
+        }
+        __syncthreads();
+        bool left = false;
+        for (int i = tid; i < n_ap; i += WIN_T) {
+            if (s_apconn[i]) continue;
+            const unsigned pin = s_appin[i];
+            bool on = false;
+            for (int j = i; j >= 0 && s_appin[j] == pin && !on; j--) on = s_apon[j] != 0;
+            for (int j = i + 1; j < n_ap && s_appin[j] == pin && !on; j++) on = s_apon[j] != 0;
+            if (on) { s_apconn[i] = 1; if (rank == 0) d.ap_conn[aoff + i] = 1; }
+            else left = true;
+        }
+        const int more = __syncthreads_or(left) && go_on;
 #ifdef WIN_PHASE_SPLIT
         sp[5] += clock64() - tq0;           // target choice, exit test, backtrace, commit, pin bookkeeping
 #endif
-        const int more = (C > 1) ? *cluster.map_shared_rank(&s_flag[3], 0) : s_flag[3];
         if (!more) break;
         if (first) {
             // after the first connection only the path is the tree: the unused APs of the
