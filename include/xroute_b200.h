@@ -26,6 +26,8 @@
  *   build_3Dgrid(data, routed_nets, bool_inference)         xr_build_obs_from_nodes
  *     baseline/build_3Dgrid.py:224-270 (eval servers,
  *     baseline/PPO/test_PPO.py:62)
+ *   Game.get_feature: 22 features per net (A3C flavour)     xr_buffer_dlpack(XR_BUF_NETFEAT)
+ *     baseline/A3C/utils.py:212-277
  *
  * Conventions: plain C types only; every function returns 0 on success or a
  * negative XR_E_* code (message via xr_last_error); no exceptions cross the
