@@ -775,27 +775,19 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             int rc = launch_route_win(env, sg, CS[b], b >= NB_BAND, nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);
             if (rc != XR_OK) return rc;
         }
-        // step epilogue.  With the full observation rebuild (obs_mode 1: gigabytes of HBM writes) every group runs
-        // its own, so that the light groups' HBM work overlaps the heavy group's on-chip routing; with the in-place
-        // incremental update the epilogue is tens of microseconds and runs once, over all environments, after the join
-        if (env->obs_mode == 1) {
-            if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
-            { Launch L(env, XR_K_MISC, sg); k_finalize<<<(g.N + 127) / 128, 128, 0, sg>>>(env->g, env->d, grp); }
-            if (has) {
-                Launch L(env, XR_K_OBS, sg);
+        if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
+        { Launch L(env, XR_K_MISC, sg); k_finalize<<<(g.N + 127) / 128, 128, 0, sg>>>(env->g, env->d, grp); }
+        if (has) {
+            Launch L(env, XR_K_OBS, sg);
+            if (env->obs_mode == 1) {
                 const long long total = (2ll + 7ll * maxn_grp[grp]) * g.cells;
                 k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, sg>>>(env->g, env->d, grp + 2);
-            }
+            } else k_obs_update<<<g.N, 256, 0, sg>>>(env->g, env->d, grp + 2);
         }
         if (split) { CK(cudaEventRecord(env->ev_join[grp], sg)); CK(cudaStreamWaitEvent(st, env->ev_join[grp], 0)); }
     }
-    env->cur_grp = -1;
-    if (env->obs_mode != 1) {
-        { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -3); }
-        { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -3); }
-        { Launch L(env, XR_K_OBS, st); k_obs_update<<<g.N, 256, 0, st>>>(env->g, env->d, 5); }
-    }
     CK(cudaGetLastError());
+    env->cur_grp = -1;
     // ---- environments whose window search escaped, or whose window does not fit on chip,
     // are routed by the full-grid sweeps and finalised in a last pass
     bool need_global = any_global;

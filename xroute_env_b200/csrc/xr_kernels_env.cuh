@@ -15,10 +15,9 @@
 // pass < 0: everything still pending (after the full-grid route loop).  Tag = pass + 2 / 1.
 __device__ __forceinline__ bool pass_selects(const Dev &d, int env, int pass) {
     if (d.fin[env] != 0) return false;
-    if (pass == -3) return d.phase[env] == 0;           // -3: every group at once, environments whose route is complete
     return pass < 0 || (d.grp[env] == pass && d.phase[env] == 0);
 }
-__device__ __forceinline__ int pass_tag(int pass) { return pass == -3 ? 5 : pass < 0 ? 1 : pass + 2; }
+__device__ __forceinline__ int pass_tag(int pass) { return pass < 0 ? 1 : pass + 2; }
 
 #define OBS_THREADS 256
 #define OBS_F4_PER_THREAD 16
