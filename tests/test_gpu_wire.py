@@ -60,3 +60,42 @@ def test_vecgame_served_over_the_wire():
     assert not errors, errors
     assert sum(s.steps for s in servers) == 2 * sum(len(i.net_ids) for i in insts)
     assert disp.batches <= sum(s.steps for s in servers)
+
+
+def test_serve_cli_plays_an_episode():
+    """`python -m xroute_env_b200.serve` (what replaces launch_training.py + the simulator container): an agent-side
+    protocol client connects to environment 1 of a 2-environment server and plays a whole episode."""
+    pytest.importorskip("zmq")
+    import os
+    import subprocess
+    import sys
+    import time
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200.instances import preset_geometry
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dp, cp = free_ports(2)
+    dp, cp = dp - 1, cp - 1                                   # environment 1 listens on base + 1
+    proc = subprocess.Popen([sys.executable, "-m", "xroute_env_b200.serve", "--preset", "T1-1x1", "--envs", "2", "--nets", "5",
+                             "--seed", "3", "--data-port", str(dp), "--ctrl-port", str(cp), "--seconds", "60", "--sparse"],
+                            cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        line = proc.stdout.readline()
+        assert line.startswith("serving 2 environment(s) 25x26x9"), line
+        geom = preset_geometry("T1-1x1")
+        inst = make_batch(geom, 2, 5, 3)[1]
+        orc = OracleEnv(geom, inst)
+        cli = WireClient(dp + 1, cp + 1)
+        msg = cli.reset()
+        assert [n + 1 for n in msg["nets"]] == inst.net_ids
+        for net in np.random.default_rng(0).permutation(inst.net_ids):
+            msg = cli.step(int(net))
+            m = orc.step(int(net))
+            assert msg["metrics"] == [m["violation"], m["wirelength"], m["via"]]
+        assert msg["is_done"]
+        cli.close()
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=10)
+        except Exception:
+            proc.kill()
