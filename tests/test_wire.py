@@ -194,3 +194,40 @@ def test_batch_dispatcher_gathers_concurrent_actions():
     d.close()
     assert d.batches < 4, "concurrent submissions must share batched steps"
     assert sum(int(c.sum()) for c in vg.calls) == 1 + 2 + 3 + 4 and out == {e: [e + 1] * 3 for e in range(4)}
+
+
+def test_evaluation_mode_drives_a_bare_rep_loop():
+    """The protocol of the reference's inference servers (baseline/PPO/test_PPO.py:50-86): the agent only answers
+    Requests on a REP socket; the simulator side starts by itself, never sends is_done and moves on to the next
+    episode when no net is left."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import build_3Dgrid  # noqa: F401  (the GPU drop-in is exercised in tests/test_gpu_wire.py)
+    g = ispd18_geometry(12, 11, 4)
+    inst = make_instance(g, 4, 44)
+    dp, = free_ports(1)
+    ctx = zmq.Context()
+    rep = ctx.socket(zmq.REP)
+    rep.bind(f"tcp://127.0.0.1:{dp}")
+    srv = SimulatorServer(OracleBackend(g, inst), data_port=dp, evaluation=True, max_episodes=2, dense=False).start()
+    try:
+        poller = zmq.Poller(); poller.register(rep, zmq.POLLIN)
+        seen = []
+        orc = OracleEnv(g, inst)
+        for k in range(2 * len(inst.net_ids)):
+            assert poller.poll(5000), "no request from the simulator side"
+            kind, msg = decode_message(rep.recv())
+            assert kind == "request" and not msg["is_done"]
+            if k % len(inst.net_ids) == 0:
+                orc.reset()
+                assert msg["metrics"] == [0, 0, 0]
+            assert [n + 1 for n in msg["nets"]] == orc.remaining()
+            data = request_to_data(msg)                                  # what handle_messange would hand to build_3Dgrid
+            assert data[3] == orc.remaining() and data[0] == [g.X, g.Y, g.Z]
+            net = msg["nets"][-1] + 1                                    # "policy": always the largest remaining id
+            seen.append(net)
+            orc.step(net)
+            rep.send(encode_response(net - 1))
+        assert not poller.poll(300)                                      # two episodes played, the server is done
+        assert srv.episodes == 2 and srv.steps == 2 * len(inst.net_ids) and seen[: len(inst.net_ids)] == sorted(inst.net_ids, reverse=True)
+    finally:
+        srv.close(); rep.close(0); ctx.term()

@@ -28,6 +28,8 @@ def main(argv=None):
     ap.add_argument("--data-port", type=int, default=5556)
     ap.add_argument("--ctrl-port", type=int, default=6667)
     ap.add_argument("--sparse", action="store_true", help="send only blockage / access / used nodes")
+    ap.add_argument("--evaluation", action="store_true",
+                    help="drive an inference server (test_PPO.py / test_DQN.py): no control socket, no is_done message")
     ap.add_argument("--seconds", type=float, default=0.0, help="exit after this long (0 = serve until interrupted)")
     args = ap.parse_args(argv)
 
@@ -46,7 +48,7 @@ def main(argv=None):
     vg.reset()
     disp = BatchDispatcher(vg) if args.envs > 1 else None
     servers = [SimulatorServer(VecGameBackend(vg, e, disp), data_port=args.data_port + e, ctrl_port=args.ctrl_port + e,
-                               dense=not args.sparse).start() for e in range(args.envs)]
+                               dense=not args.sparse, evaluation=args.evaluation).start() for e in range(args.envs)]
     print(f"serving {args.envs} environment(s) {geom.X}x{geom.Y}x{geom.Z}: data ports {args.data_port}.., "
           f"control ports {args.ctrl_port}..", flush=True)
     t0 = time.time()

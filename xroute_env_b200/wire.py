@@ -328,10 +328,14 @@ class SimulatorServer:
     """
 
     def __init__(self, backend, data_port: int = 5556, ctrl_port: int = 6667, host: str = "127.0.0.1",
-                 dense: bool = True):
+                 dense: bool = True, evaluation: bool = False, max_episodes: int = 0):
         import zmq
         self.zmq = zmq
         self.backend, self.data_port, self.ctrl_port, self.host, self.dense = backend, data_port, ctrl_port, host, dense
+        # evaluation mode: the protocol of the reference's inference servers (baseline/PPO/test_PPO.py:50-86,
+        # baseline/DQN/test_DQN.py): a bare REP loop on the agent side, no control socket and no is_done message --
+        # the simulator walks through its regions by itself (examples/launch_evaluation.py)
+        self.evaluation, self.max_episodes = evaluation, max_episodes
         self.ctx = zmq.Context()
         self.episodes = 0
         self.steps = 0
@@ -341,6 +345,12 @@ class SimulatorServer:
         self._threads = []
 
     def start(self):
+        if self.evaluation:
+            self.ctrl = None
+            t = threading.Thread(target=self._evaluation_loop, daemon=True)
+            t.start()
+            self._threads.append(t)
+            return self
         self.ctrl = self.ctx.socket(self.zmq.REP)
         self.ctrl.bind(f"tcp://{self.host}:{self.ctrl_port}")
         t = threading.Thread(target=self._ctrl_loop, daemon=True)
@@ -360,6 +370,31 @@ class SimulatorServer:
             t = threading.Thread(target=self._episode, args=(self._gen,), daemon=True)
             t.start()
             self._threads.append(t)
+
+    def _evaluation_loop(self):
+        zmq = self.zmq
+        sock = self.ctx.socket(zmq.REQ)
+        sock.setsockopt(zmq.LINGER, 0)
+        sock.connect(f"tcp://{self.host}:{self.data_port}")
+        poller = zmq.Poller()
+        poller.register(sock, zmq.POLLIN)
+        try:
+            while not self._stop.is_set() and (self.max_episodes <= 0 or self.episodes < self.max_episodes):
+                self.backend.reset()
+                self.episodes += 1
+                while not self._stop.is_set() and self.backend.remaining():
+                    sock.send(self._snapshot(is_done=False))
+                    while not poller.poll(50):
+                        if self._stop.is_set():
+                            return
+                    kind, idx = decode_message(sock.recv())
+                    self.log.append((self.episodes, idx))
+                    if idx < 0:
+                        break
+                    self.backend.step(idx + 1)
+                    self.steps += 1
+        finally:
+            sock.close(0)
 
     def _snapshot(self, is_done: bool) -> bytes:
         b = self.backend
@@ -402,7 +437,8 @@ class SimulatorServer:
         for t in self._threads:
             t.join(timeout=2)
         try:
-            self.ctrl.close(0)
+            if self.ctrl is not None:
+                self.ctrl.close(0)
         except Exception:
             pass
         self.ctx.term()
