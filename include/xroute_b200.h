@@ -66,7 +66,8 @@ typedef struct XrConfig {
     int32_t max_nets;          /* largest net id any instance may use                        */
     int32_t max_aps;           /* access points per environment, upper bound                 */
     int32_t obs_max_nets;      /* nets materialised in the observation; <0 = max_nets        */
-    int32_t path_capacity;     /* path cells kept per env for xr_get_paths; 0 = default      */
+    int32_t path_capacity;     /* path cells of ONE net kept per env (xr_get_paths; the router reads them back: a net
+                                  whose paths exceed it fails the step with XR_E_CAPACITY); 0 = 16(X+Y+Z)+1024 */
     const int32_t *x_coords;   /* [X] DBU, strictly increasing                               */
     const int32_t *y_coords;   /* [Y]                                                        */
     const uint8_t *layer_dir;  /* [Z] 0 = horizontal (preferred axis x), 1 = vertical        */

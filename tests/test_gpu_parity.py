@@ -122,6 +122,66 @@ def test_dual_cyclic_layout_kernel(minc, cluster, monkeypatch):
     _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, min_cluster=cluster, check_obs_every=4)
 
 
+def _own_walk_case():
+    """Layer 0 is horizontal with x pitch 300 and y pitch 100, so an x step (300) costs exactly a y step
+    (100 x (1 + GRIDCOST)).  Net 1: the walk back from (2,6,0) runs along row 6 to (5,6,0), whose only real predecessor is the
+    source (5,5,0) below it -- but the cell it just left, (4,6,0), is one x step away too.  Net 2: the same on a later
+    connection (three pins: the walk from (7,11,0) meets the tree at (9,10,0) from (9,11,0)); net 3: a control."""
+    from xroute_env_b200.instances import Instance
+    geom = ispd18_geometry(14, 16, 3)
+    geom.x_coords = (300 * np.arange(14)).astype(np.int32)
+    geom.y_coords = (100 * np.arange(16)).astype(np.int32)
+    aps = [(1, 1, 5, 5, 0), (1, 2, 2, 6, 0),
+           (2, 1, 9, 10, 0), (2, 2, 12, 10, 0), (2, 3, 7, 11, 0),
+           (3, 1, 3, 12, 0), (3, 2, 2, 9, 0)]
+    a = np.array(aps, np.int32)
+    inst = Instance(block_xyz=np.zeros((0, 3), np.int32), ap_net=a[:, 0].copy(), ap_pin=a[:, 1].copy(),
+                    ap_xyz=np.ascontiguousarray(a[:, 2:5]))
+    return geom, inst
+
+
+@pytest.mark.parametrize("engine", ["band", "dual", "global"])
+def test_backtrace_ignores_the_cells_of_its_own_walk(engine, monkeypatch):
+    """Found by tools/fuzz_parity.py (non-uniform grid, configuration 762 of seed 7): every engine used to turn the
+    cells of a walk into sources (distance 0) while still walking, and a later cell of the same walk could then accept
+    the cell it had just left as predecessor (0 + w == dist) ahead of the real source in the canonical order."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    geom, inst = _own_walk_case()
+    kw = dict(min_cluster=2)
+    if engine == "dual":
+        monkeypatch.setenv("XR_DUAL_PINS", "2"); monkeypatch.setenv("XR_DUAL_MINC", "2")
+    if engine == "global":
+        kw = dict(window_margin=-1)
+    vg = VecGame(geom, [inst], device=0, **kw)
+    vg.reset()
+    orc = OracleEnv(geom, inst)
+    for net in (1, 2, 3):
+        vg.step(np.array([net], np.int32))
+        orc.step(net)
+        oc, oo, ocost = orc.last_paths()
+        gc, go, gcost = vg.paths(0)
+        assert np.array_equal(ocost, gcost) and np.array_equal(oo, go), net
+        assert np.array_equal(oc, gc), (net, oc.tolist(), gc.tolist())
+        assert len(set(gc[go[0]:go[1]].tolist())) == go[1] - go[0], "a path visits a cell twice"
+    assert np.array_equal(vg.state(0)[0], orc.state()[0])
+    vg.close()
+
+
+def test_path_capacity_overflow_fails_the_step():
+    """The router reads a net's new tree cells back from the path record: a record too small for the net is an error
+    of the step (XR_E_CAPACITY), never a silently different route."""
+    from xroute_env_b200 import VecGame
+    geom = ispd18_geometry(40, 40, 3)
+    insts = make_batch(geom, 1, 4, seed=5)
+    vg = VecGame(geom, insts, device=0, path_capacity=3)
+    vg.reset()
+    with pytest.raises(RuntimeError, match="path_capacity"):
+        for net in insts[0].net_ids:
+            vg.step(np.array([net], np.int32))
+    vg.close()
+
+
 def test_window_fallback_counter_and_exactness():
     from xroute_env_b200 import VecGame
     geom = ispd18_geometry(64, 64, 9)

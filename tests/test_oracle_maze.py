@@ -89,6 +89,26 @@ def test_tie_break_is_canonical():
     assert cells[off[0]] == ci(g, 0, 2, 0) and cells[off[1]] == ci(g, 4, 2, 0)
 
 
+def test_backtrace_reads_the_converged_field_only():
+    """x pitch 300 / y pitch 100 on a horizontal layer: an x step costs what a wrong-way y step costs (100 * 3).  The walk
+    back from (2,6) runs along row 6 to (5,6); there the cell it just left is one x step away, and so is the source
+    (5,5) one y step below.  The path is read from the converged distance field, so it never turns back: it ends on
+    the source (the GPU engines once differed here, tests/test_gpu_parity.py::test_backtrace_ignores_...)."""
+    g = ispd18_geometry(14, 16, 3)
+    g.x_coords = (300 * np.arange(14)).astype(np.int32)
+    g.y_coords = (100 * np.arange(16)).astype(np.int32)
+    aps = [(1, 1, (5, 5, 0)), (1, 2, (2, 6, 0)), (2, 1, (9, 10, 0)), (2, 2, (12, 10, 0)), (2, 3, (7, 11, 0))]
+    env = OracleEnv(g, _inst([], aps))
+    env.step(1)
+    cells, off, cost = env.last_paths()
+    assert cost.tolist() == [1200]
+    assert cells.tolist() == [ci(g, 2, 6, 0), ci(g, 3, 6, 0), ci(g, 4, 6, 0), ci(g, 5, 6, 0), ci(g, 5, 5, 0)]
+    env.step(2)
+    cells, off, cost = env.last_paths()
+    assert cost.tolist() == [900, 900]
+    assert cells[off[1]:].tolist() == [ci(g, 7, 11, 0), ci(g, 8, 11, 0), ci(g, 9, 11, 0), ci(g, 9, 10, 0)]
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_distance_field_matches_brute_force(seed):
     rng = np.random.default_rng(seed)

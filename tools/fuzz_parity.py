@@ -1,0 +1,62 @@
+"""Randomised parity campaign: random grid shapes (uniform and non-uniform pitch), obstacle densities, net counts and
+engine settings; every connection cost, path, metric and the final occupancy against the CPU oracle.
+    python tools/fuzz_parity.py [seconds] [seed]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from xroute_env_b200 import VecGame, make_batch, ispd18_geometry
+from oracle.oracle import OracleEnv
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+t0, n_cfg, n_steps, bad = time.time(), 0, 0, []
+while time.time() - t0 < budget and not bad:
+    X, Y, Z = int(rng.integers(8, 130)), int(rng.integers(8, 130)), int(rng.integers(2, 10))
+    geom = ispd18_geometry(X, Y, Z)
+    if rng.random() < 0.4:
+        geom.x_coords = np.cumsum(rng.integers(60, 900, X)).astype(np.int32)
+        geom.y_coords = np.cumsum(rng.integers(60, 900, Y)).astype(np.int32)
+    n_env, n_nets = int(rng.integers(2, 7)), int(rng.integers(2, 11))
+    iseed, pob = int(rng.integers(1 << 30)), float(rng.choice([0.0, 0.1, 0.25, 0.4]))
+    uniform = len(set(np.diff(geom.x_coords).tolist())) == 1
+    try:
+        insts = make_batch(geom, n_env, n_nets, seed=iseed, p_obstacle=pob)
+    except RuntimeError:
+        continue
+    kw = dict(window_margin=int(rng.choice([-1, 0, 0, 0, 1, 4, 30])), min_cluster=int(rng.choice([0, 0, 1, 2, 4, 8, 16])),
+              obs_mode=int(rng.choice([0, 0, 1])))
+    dual = rng.random() < 0.5
+    for k, v in (("XR_DUAL_PINS", "2" if dual else "8"), ("XR_DUAL_MINC", str(int(rng.choice([2, 4, 8]))) if dual else "8")):
+        os.environ[k] = v
+    vg = VecGame(geom, insts, device=0, **kw)
+    vg.reset()
+    orcs = [OracleEnv(geom, i) for i in insts]
+    orders = [list(rng.permutation(i.net_ids)) for i in insts]
+    for t in range(max(len(o) for o in orders)):
+        acts = np.array([int(o[t]) if t < len(o) else 0 for o in orders], np.int32)
+        vg.step(acts)
+        delta, done, cum = vg.results_host()
+        for e, o in enumerate(orcs):
+            if acts[e] == 0:
+                continue
+            m = o.step(int(acts[e]))
+            oc, oo, ocost = o.last_paths(); gc, go, gcost = vg.paths(e)
+            ok = (np.array_equal(oc, gc) and np.array_equal(ocost, gcost) and
+                  [int(v) for v in cum[e]] == [m["violation"], m["wirelength"], m["via"], m["blocked"], m["shorted"], m["overflow"]])
+            if ok and (t % 3 == 0 or m["done"]):
+                ok = np.array_equal(vg.obs_host(e).numpy(), o.obs())
+            if not ok:
+                pins = len(set(insts[e].ap_pin[insts[e].ap_net == acts[e]].tolist()))
+                bad.append(dict(shape=(X, Y, Z), uniform=uniform, n_env=n_env, n_nets=n_nets, iseed=iseed, pob=pob, kw=kw, dual=dual,
+                                minc=os.environ["XR_DUAL_MINC"], t=t, e=e, net=int(acts[e]), pins=pins,
+                                cost_o=ocost.tolist()[:6], cost_g=gcost.tolist()[:6], path_eq=bool(np.array_equal(oc, gc)),
+                                cum_g=[int(v) for v in cum[e]], cum_o=[m["violation"], m["wirelength"], m["via"]],
+                                rc=vg.route_counters()))
+            n_steps += 1
+    for e, o in enumerate(orcs):
+        if not (np.array_equal(vg.state(e)[0], o.state()[0]) and np.array_equal(vg.state(e)[1], o.state()[1])):
+            bad.append(dict(shape=(X, Y, Z), kw=kw, dual=dual, what="state", e=e))
+    vg.close()
+    n_cfg += 1
+print(f"fuzz: {n_cfg} configurations, {n_steps} env-steps in {time.time() - t0:.0f}s:", "ALL BIT-EXACT" if not bad else f"MISMATCH {bad[:3]}")
+sys.exit(1 if bad else 0)

@@ -205,7 +205,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     g.cells_o = (g.cells + 15) / 16 * 16;
     g.max_nets = cfg->max_nets; g.max_aps = cfg->max_aps;
     g.obs_max_nets = (cfg->obs_max_nets < 0 || cfg->obs_max_nets > cfg->max_nets) ? cfg->max_nets : cfg->obs_max_nets;
-    g.path_cap = cfg->path_capacity > 0 ? cfg->path_capacity : 8 * (cfg->X + cfg->Y + cfg->Z) + 256;
+    g.path_cap = cfg->path_capacity > 0 ? cfg->path_capacity : 16 * (cfg->X + cfg->Y + cfg->Z) + 1024;
     g.conn_cap = 256;
     const long long maxc = 2ll + 7ll * g.obs_max_nets;
     g.obs_stride = (maxc * g.cells + 63) / 64 * 64;
@@ -798,7 +798,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         CK(cudaStreamSynchronize(st)); env->n_sync++;
         memcpy(env->p_flags, env->p_res + sizeof(int64_t) * XR_M_COUNT * g.N + sizeof(int32_t) * 3 * g.N, sizeof(int32_t) * 2);
         if (env->p_flags[1] != 0) {
+            const bool cap = env->p_flags[1] == 4;
             cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
+            if (cap) return fail(env, XR_E_CAPACITY, "a net's paths exceed path_capacity (XrConfig.path_capacity)");
             return fail(env, XR_E_UNROUTABLE, "window maze search failed (inconsistent backtrace)");
         }
         if (env->p_flags[0] > 0) need_global = true;
@@ -817,7 +819,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st)); env->n_sync++;
             if (env->p_flags[1] != 0) {
+                const bool cap = env->p_flags[1] == 4;
                 cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
+                if (cap) return fail(env, XR_E_CAPACITY, "a net's paths exceed path_capacity (XrConfig.path_capacity)");
                 return fail(env, XR_E_UNROUTABLE, "maze search failed (no path / inconsistent backtrace)");
             }
             if (env->p_flags[0] == 0) break;

@@ -395,6 +395,10 @@ __device__ __forceinline__ uint32_t move_w(const Geo &g, int px, int py, int pz,
 }
 
 // Commit one path cell: occupancy, obstacle channel source, tree mark, new source.
+// zero_dist = false: the caller is still walking the distance field (full-grid backtrace) and turns the path cells into
+// sources only after the walk -- a cell that became 0 under the walk could pass the predecessor test of a later cell
+// (found by tools/fuzz_parity.py on a non-uniform grid: x step == 3 * y step next to the source).
+template <bool zero_dist = true>
 __device__ __forceinline__ void commit_cell(const Geo &g, const Dev &d, int env, int net, int x, int y, int z) {
     const size_t c = (size_t)env * g.cells_p + ((size_t)z * g.Y + y) * g.Xp + x;
     uint32_t ci = d.cellinfo[c];
@@ -405,7 +409,7 @@ __device__ __forceinline__ void commit_cell(const Geo &g, const Dev &d, int env,
     d.obst_obs[(size_t)env * g.cells_o + oo] = 1;
     d.obs[(size_t)env * g.obs_stride + oo] = 1.f;        // channel 0 of the observation, updated in place
     d.cflag[c] |= CF_TREE;
-    d.dist[c] = 0;
+    if (zero_dist) d.dist[c] = 0;
     d.g_rowd[(size_t)env * g.Y + y] = 1;                    // full-grid path: the new source's lines are dirty
     d.g_slabd[((size_t)env * g.Z + z) * (g.Xp / 32) + (x >> 5)] = 1;
 }
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
     int cx = cp % g.Xp, cy = (cp / g.Xp) % g.Y, cz = cp / (g.Xp * g.Y);
     // ---- canonical backtrace + commit
     int pn = d.path_n[env];
+    const int pn0 = pn;
     const int cn = d.conn_n[env];
     int *path = d.path + (size_t)env * g.path_cap;
     long long wl = 0, via = 0;
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
             run = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
             if (run > 0) {
                 if (lane < run) {
-                    commit_cell(g, d, env, net, ax, ay, az);
+                    commit_cell<false>(g, d, env, net, ax, ay, az);
                     if (pn + lane < g.path_cap) path[pn + lane] = (az * g.Y + ay) * g.X + ax;
                     if (last >= 4) via += 1;
                     else if (last < 2) wl += abs(g.xc[ax] - g.xc[bx]);
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
             if (m == 0u) { fail = true; break; }
             const int dir = __ffs(m) - 1;
             if (lane == dir) {
-                commit_cell(g, d, env, net, cx, cy, cz);
+                commit_cell<false>(g, d, env, net, cx, cy, cz);
                 if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                 if (dir >= 4) via += 1;
                 else if (dir < 2) wl += abs(g.xc[cx] - g.xc[px]);
@@ -533,11 +538,21 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
     // first connection, when it is a source-pin AP that is not on the tree yet
     if (!fail) {
         if (lane == 0) {
-            if (first) commit_cell(g, d, env, net, cx, cy, cz);
+            if (first) commit_cell<false>(g, d, env, net, cx, cy, cz);
             if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
         }
         pn += 1;
     }
+    // the walk is over: its cells become sources of the next connection (read back from the path record, which must
+    // therefore hold the whole net: an overflow is an error of the step, XR_E_CAPACITY)
+    __syncwarp();
+    const bool over = pn > g.path_cap;
+    for (int k = pn0 + lane; k < (over ? g.path_cap : pn); k += 32) {
+        const int ci = path[k];
+        const int x = ci % g.X, y = (ci / g.X) % g.Y, z = ci / (g.X * g.Y);
+        d.dist[eoff + ((size_t)z * g.Y + y) * g.Xp + x] = 0;
+    }
+    fail |= over;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         wl += __shfl_xor_sync(0xFFFFFFFFu, wl, off);
@@ -591,7 +606,7 @@ __global__ void __launch_bounds__(32) k_control(Geo g, Dev d) {
         }
         d.conn_n[env] = cn + 1;
         d.envstat[8 * (size_t)env + 3] += 1;
-        if (fail) d.flags[1] = 2;
+        if (fail) d.flags[1] = over ? 4 : 2;
         if (left && !fail) {
             d.changed[env] = 1;
             d.reinit[env] = first ? 1 : 0;

@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             int cp = (int)(best & 0xFFFFFFFFu);
             int cx = cp % g.Xp, cy = (cp / g.Xp) % g.Y, cz = cp / (g.Xp * g.Y);
             int pn = d.path_n[env];
+            const int pn0 = pn;
             const int cn = d.conn_n[env];
             int *path = d.path + (size_t)env * g.path_cap;
             long long wl = 0, via = 0;
@@ -663,7 +664,6 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                         if (pend + 32 > WIN_TGT_CAP) flush();
                         if (lane < run) {
                             s_tloc[pend + lane] = (uint32_t)((ax - wx0) | ((ay - wy0) << 10) | (az << 20));
-                            win2_set_tree<C>(cluster, c, ax - wx0, ay - wy0, az, va);
                             if (pn + lane < g.path_cap) path[pn + lane] = (az * g.Y + ay) * g.X + ax;
                             if (last >= 4) via += 1;
                             else if (last < 2) wl += abs(g.xc[ax] - g.xc[bx]);
@@ -690,7 +690,6 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                 if (pend + 1 > WIN_TGT_CAP) flush();
                 if (lane == dir) {
                     s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
-                    win2_set_tree<C>(cluster, c, cx - wx0, cy - wy0, cz, vc);
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                     if (dir >= 4) via += 1;
                     else if (dir < 2) wl += abs(g.xc[cx] - g.xc[px]);
@@ -705,16 +704,25 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             if (!fail) {                                 // the cell the walk ended on joins the tree on the first connection only
                 if (first && pend + 1 > WIN_TGT_CAP) flush();
                 if (lane == 0) {
-                    if (first) {
-                        s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
-                        win2_set_tree<C>(cluster, c, cx - wx0, cy - wy0, cz, *win2_cellA<C>(cluster, c, cx - wx0, cy - wy0, cz));
-                    }
+                    if (first) s_tloc[pend] = (uint32_t)((cx - wx0) | ((cy - wy0) << 10) | (cz << 20));
                     if (pn < g.path_cap) path[pn] = (cz * g.Y + cy) * g.X + cx;
                 }
                 pn += 1;
                 if (first) pend += 1;
             }
             flush();
+            // The walk is over: only now do its cells join the tree on chip, in both layouts (distance 0, tree bit, dirty
+            // lines) -- a cell zeroed under the walk could pass the predecessor test of a later cell.  They are read
+            // back from the path record, which must therefore hold the whole net (an overflow fails the step with
+            // XR_E_CAPACITY).  The cell the walk ended on is a source already; on the first connection it gets its
+            // tree bit here.
+            const bool over = pn > g.path_cap;
+            for (int k = pn0 + lane; k < (over ? g.path_cap : pn); k += 32) {
+                const int ci = path[k];
+                const int x = ci % g.X - wx0, y = (ci / g.X) % g.Y - wy0, z = ci / (g.X * g.Y);
+                win2_set_tree<C>(cluster, c, x, y, z, *win2_cellA<C>(cluster, c, x, y, z));
+            }
+            fail |= over;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 wl += __shfl_xor_sync(0xFFFFFFFFu, wl, off);
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
                 }
                 d.conn_n[env] = cn + 1;
                 d.envstat[8 * (size_t)env + 3] += 1;
-                if (fail) d.flags[1] = 3;
+                if (fail) d.flags[1] = over ? 4 : 3;
                 s_flag[3] = fail ? 0 : 1;
             }
         }
