@@ -82,6 +82,73 @@ def brute_force_dist(geom, cflag, sources):
         d = nd
 
 
+def spec_route_net(geom, inst, usage, owner, net):
+    """Second, independent restatement of SPEC steps 1-3 in plain Python on top of the dense
+    Bellman-Ford above -- no code shared with oracle/xr_oracle.c: source pin, all-targets search, canonical target,
+    canonical backtrace on the converged field, commit.  usage / owner [Z,Y,X] are updated in place.
+    Returns (cells, conn_off, conn_cost, d_wirelength, d_via) like OracleEnv.last_paths()."""
+    Z, Y, X = usage.shape
+    xc, yc = geom.x_coords.astype(np.int64), geom.y_coords.astype(np.int64)
+    aps = [(int(p), tuple(int(v) for v in xyz)) for n, p, xyz in zip(inst.ap_net, inst.ap_pin, inst.ap_xyz) if n == net]
+    pins = sorted(set(p for p, _ in aps))
+    if len(pins) < 2:
+        return [], [0], [], 0, 0
+    apnet = np.zeros((Z, Y, X), np.int64)
+    for n, (x, y, z) in zip(inst.ap_net, inst.ap_xyz):
+        apnet[z, y, x] = n
+    blk = np.zeros((Z, Y, X), np.uint8)
+    for x, y, z in inst.block_xyz:
+        blk[z, y, x] = 1
+    cflag = ((usage > 0).astype(np.uint8) | (((apnet != 0) & (apnet != net)).astype(np.uint8) << 1) | (blk << 2))
+
+    def w(p, c):                                          # weight of entering c from p
+        (px, py, pz), (cx, cy, cz) = p, c
+        f = int(cflag[cz, cy, cx])
+        mult = 1 + geom.drc_cost * (f & 1) + geom.fixed_shape_cost * ((f >> 1) & 1)
+        pen = geom.block_cost * int(geom.layer_min_width[cz]) * 20 * ((f >> 2) & 1)
+        if pz != cz:
+            return geom.via_cost * int(geom.layer_pitch[max(pz, cz)]) * mult + pen
+        axis = 0 if px != cx else 1
+        length = abs(int(xc[cx] - xc[px])) + abs(int(yc[cy] - yc[py]))
+        return length * (mult + geom.grid_cost * (axis != int(geom.layer_dir[cz]))) + pen
+
+    xs, ys = [a[1][0] for a in aps], [a[1][1] for a in aps]
+    cx2, cy2 = min(xs) + max(xs), min(ys) + max(ys)
+    src_pin = min((abs(2 * x - cx2) + abs(2 * y - cy2), p) for p, (x, y, z) in aps)[1]
+    tree = [xyz for p, xyz in aps if p == src_pin]
+    connected = {src_pin}
+    DELTA = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    cells, off, costs, wl, via, first = [], [0], [], 0, 0, True
+    while len(connected) < len(pins):
+        d = brute_force_dist(geom, cflag, tree)
+        tgt = min((int(d[z, y, x]), (z * Y + y) * X + x, (x, y, z)) for p, (x, y, z) in aps if p not in connected)
+        costs.append(tgt[0])
+        c, last, path = tgt[2], None, [tgt[2]]
+        while d[c[2], c[1], c[0]] != 0:
+            for k in ([last] if last is not None else []) + list(range(6)):
+                p = (c[0] - DELTA[k][0], c[1] - DELTA[k][1], c[2] - DELTA[k][2])
+                if 0 <= p[0] < X and 0 <= p[1] < Y and 0 <= p[2] < Z and d[p[2], p[1], p[0]] + w(p, c) == d[c[2], c[1], c[0]]:
+                    break
+            else:
+                raise AssertionError("no predecessor")
+            c, last = p, k
+            path.append(c)
+        for u, v in zip(path[:-1], path[1:]):
+            via += u[2] != v[2]
+            wl += abs(int(xc[u[0]] - xc[v[0]])) + abs(int(yc[u[1]] - yc[v[1]]))
+        for (x, y, z) in (path if first else path[:-1]):
+            usage[z, y, x] = min(255, int(usage[z, y, x]) + 1)
+            if owner[z, y, x] == 0:
+                owner[z, y, x] = net
+        tree = (path if first else tree + path)
+        first = False
+        on = set(tree)
+        connected |= {p for p, xyz in aps if xyz in on}
+        cells += [(z * Y + y) * X + x for (x, y, z) in path]
+        off.append(len(cells))
+    return cells, off, costs, wl, via
+
+
 class OracleBackend:
     """Simulator state for xroute_env_b200.wire.SimulatorServer backed by the CPU oracle
     (test infrastructure: lets the wire layer be exercised without a GPU)."""

@@ -4,7 +4,7 @@ answers and (b) an independent dense numpy Bellman-Ford restatement of the SPEC.
 import numpy as np
 import pytest
 
-from helpers import brute_force_dist
+from helpers import brute_force_dist, spec_route_net
 from oracle.oracle import OracleEnv
 from xroute_env_b200.instances import Instance, ispd18_geometry, make_instance
 
@@ -166,3 +166,32 @@ def test_paths_are_consistent_with_costs_and_metrics(seed):
         assert ma["violation"] == ma["blocked"] + ma["shorted"]
     with pytest.raises(ValueError):
         a.step(int(inst.net_ids[0]))                    # already routed -> illegal
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_whole_net_routing_matches_independent_restatement(seed):
+    """Targets, canonical backtrace, commit and the tree bookkeeping against a second restatement of the SPEC that shares
+    no code with the C oracle (dense Bellman-Ford + plain-Python walk), on grids made of ties: every pitch and via
+    cost a small multiple of 100, random layer directions and cost constants."""
+    rng = np.random.default_rng(100 + seed)
+    X, Y, Z = int(rng.integers(5, 13)), int(rng.integers(5, 13)), int(rng.integers(2, 5))
+    g = ispd18_geometry(X, Y, Z)
+    px, py = rng.choice([100, 200, 300], 2)
+    g.x_coords = (np.cumsum(rng.choice([1, 1, 2, 3], X)) * px).astype(np.int32)
+    g.y_coords = (py * np.arange(Y)).astype(np.int32)
+    g.layer_dir = rng.integers(0, 2, Z).astype(np.uint8)
+    g.layer_pitch = rng.choice([25, 50, 75, 100], Z).astype(np.int32)
+    g.layer_min_width = rng.choice([5, 10, 20], Z).astype(np.int32)
+    g.via_cost, g.grid_cost = int(rng.choice([1, 2, 4])), int(rng.choice([0, 1, 2]))
+    g.drc_cost, g.fixed_shape_cost, g.block_cost = int(rng.choice([1, 2, 8])), int(rng.choice([1, 2, 8])), int(rng.choice([1, 5, 32]))
+    inst = make_instance(g, 4, 300 + seed, p_obstacle=0.2)
+    env = OracleEnv(g, inst)
+    usage, owner = np.zeros((Z, Y, X), np.uint8), np.zeros((Z, Y, X), np.uint16)
+    for net in rng.permutation(inst.net_ids):
+        m = env.step(int(net))
+        cells, off, cost, wl, via = spec_route_net(g, inst, usage, owner, int(net))
+        oc, oo, ocost = env.last_paths()
+        assert ocost.tolist() == cost and oo.tolist() == off and oc.tolist() == cells, (seed, net)
+        assert (m["d_wirelength"], m["d_via"]) == (wl, via)
+        ou, oown = env.state()
+        assert np.array_equal(ou, usage) and np.array_equal(oown, owner)

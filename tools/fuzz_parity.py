@@ -1,6 +1,10 @@
 """Randomised parity campaign: random grid shapes (uniform and non-uniform pitch), obstacle densities, net counts and
 engine settings; every connection cost, path, metric and the final occupancy against the CPU oracle.
-    python tools/fuzz_parity.py [seconds] [seed]"""
+    python tools/fuzz_parity.py [seconds] [seed] [ties]
+`ties`: every pitch, via cost and penalty is a small multiple of 100 (an x step, a wrong-way y step and a via often weigh
+the same), layer directions are random and the cost constants vary -- almost every cell then has several equal-cost
+predecessors, which is what exercises the canonical target and backtrace rules (the one mismatch this campaign ever
+found needed x pitch == 3 x y pitch next to a source)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,11 +13,21 @@ from oracle.oracle import OracleEnv
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+ties = len(sys.argv) > 3 and sys.argv[3] == "ties"
 t0, n_cfg, n_steps, bad = time.time(), 0, 0, []
 while time.time() - t0 < budget and not bad:
     X, Y, Z = int(rng.integers(8, 130)), int(rng.integers(8, 130)), int(rng.integers(2, 10))
     geom = ispd18_geometry(X, Y, Z)
-    if rng.random() < 0.4:
+    if ties:
+        px, py = rng.choice([100, 200, 300], 2)
+        geom.x_coords = (np.cumsum(rng.choice([1, 1, 1, 2, 3], X)) * px).astype(np.int32) if rng.random() < 0.3 else (px * np.arange(X)).astype(np.int32)
+        geom.y_coords = (np.cumsum(rng.choice([1, 1, 1, 2, 3], Y)) * py).astype(np.int32) if rng.random() < 0.3 else (py * np.arange(Y)).astype(np.int32)
+        geom.layer_dir = rng.integers(0, 2, Z).astype(np.uint8)
+        geom.layer_pitch = rng.choice([25, 50, 75, 100], Z).astype(np.int32)
+        geom.layer_min_width = rng.choice([5, 10, 20], Z).astype(np.int32)
+        geom.via_cost, geom.grid_cost = int(rng.choice([1, 2, 4])), int(rng.choice([0, 1, 2]))
+        geom.drc_cost, geom.fixed_shape_cost, geom.block_cost = int(rng.choice([1, 2, 8])), int(rng.choice([1, 2, 8])), int(rng.choice([1, 5, 32]))
+    elif rng.random() < 0.4:
         geom.x_coords = np.cumsum(rng.integers(60, 900, X)).astype(np.int32)
         geom.y_coords = np.cumsum(rng.integers(60, 900, Y)).astype(np.int32)
     n_env, n_nets = int(rng.integers(2, 7)), int(rng.integers(2, 11))
