@@ -122,6 +122,29 @@ def test_dual_cyclic_layout_kernel(minc, cluster, monkeypatch):
     _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, min_cluster=cluster, check_obs_every=4)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_tie_heavy_grids(seed, monkeypatch):
+    """Grids made of ties (`tools/fuzz_parity.py ... ties`, fixed seeds): every pitch and via cost a small multiple of
+    100, random layer directions and cost constants -- most cells have several equal-cost predecessors, so the paths
+    rest entirely on the canonical target / backtrace rules.  Odd seeds force every net through the dual kernel."""
+    rng = np.random.default_rng(500 + seed)
+    X, Y, Z = int(rng.integers(20, 70)), int(rng.integers(20, 70)), int(rng.integers(2, 10))
+    geom = ispd18_geometry(X, Y, Z)
+    px, py = rng.choice([100, 200, 300], 2)
+    geom.x_coords = (np.cumsum(rng.choice([1, 1, 1, 2, 3], X)) * px).astype(np.int32)
+    geom.y_coords = (py * np.arange(Y)).astype(np.int32)
+    geom.layer_dir = rng.integers(0, 2, Z).astype(np.uint8)
+    geom.layer_pitch = rng.choice([25, 50, 75, 100], Z).astype(np.int32)
+    geom.layer_min_width = rng.choice([5, 10, 20], Z).astype(np.int32)
+    geom.via_cost, geom.grid_cost = int(rng.choice([1, 2, 4])), int(rng.choice([0, 1, 2]))
+    geom.drc_cost, geom.fixed_shape_cost, geom.block_cost = int(rng.choice([1, 2, 8])), int(rng.choice([1, 2, 8])), int(rng.choice([1, 5, 32]))
+    if seed % 2:
+        monkeypatch.setenv("XR_DUAL_PINS", "2"); monkeypatch.setenv("XR_DUAL_MINC", "2")
+    insts = make_batch(geom, 4, 8, seed=510 + seed, p_obstacle=0.25)
+    _run_episode(geom, insts, seed=seed, min_cluster=2 if seed < 2 else 0, check_obs_every=3)
+    _run_episode(geom, insts[:2], seed=seed, window_margin=-1, check_obs_every=8)
+
+
 def _own_walk_case():
     """Layer 0 is horizontal with x pitch 300 and y pitch 100, so an x step (300) costs exactly a y step
     (100 x (1 + GRIDCOST)).  Net 1: the walk back from (2,6,0) runs along row 6 to (5,6,0), whose only real predecessor is the
