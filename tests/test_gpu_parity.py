@@ -145,6 +145,59 @@ def test_tie_heavy_grids(seed, monkeypatch):
     _run_episode(geom, insts[:2], seed=seed, window_margin=-1, check_obs_every=8)
 
 
+def _strip_instances():
+    """Three 700 x 10 x 3 strips with the generator's blockages and six hand-placed nets whose pins sit at the two ends
+    (and, for the 3- and 4-pin nets, in the middle) of the strip."""
+    from xroute_env_b200.instances import Instance
+    geom = ispd18_geometry(700, 10, 3)
+    insts = []
+    for e, base in enumerate(make_batch(geom, 3, 6, seed=77, p_obstacle=0.15)):
+        aps = []
+        for k in range(1, 7):
+            aps += [(k, 1, 5 + 3 * k + e, (k + e) % 10, 0), (k, 2, 694 - 2 * k - e, (3 * k + e) % 10, k % 2)]
+            if k >= 4:
+                aps += [(k, 3, 300 + 17 * k, (k + 2 * e) % 10, 1), (k, 3, 301 + 17 * k, (k + 2 * e) % 10, 1)]
+            if k == 6:
+                aps += [(k, 4, 500 + e, 2, 0)]
+        a = np.array(aps, np.int32)
+        taken = set(map(tuple, a[:, 2:5].tolist()))
+        blk = np.array([b for b in base.block_xyz.tolist() if tuple(b) not in taken], np.int32).reshape(-1, 3)
+        insts.append(Instance(block_xyz=blk, ap_net=a[:, 0].copy(), ap_pin=a[:, 1].copy(), ap_xyz=np.ascontiguousarray(a[:, 2:5])))
+    return geom, insts
+
+
+@pytest.mark.parametrize("engine", ["band", "dual"])
+def test_long_paths_span_several_commit_flushes(engine, monkeypatch):
+    """A 700-track-wide strip: single connections of several hundred cells.  The window kernels stage at most 256 path
+    cells on chip before a parallel commit pass, and put the whole walk on the tree from the path record afterwards --
+    paths longer than one stage must come out bit-exact too, and stay on the window engines."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    if engine == "dual":
+        monkeypatch.setenv("XR_DUAL_PINS", "2"); monkeypatch.setenv("XR_DUAL_MINC", "2")
+    geom, insts = _strip_instances()
+    vg = VecGame(geom, insts, device=0, min_cluster=2)
+    vg.reset()
+    orcs = [OracleEnv(geom, i) for i in insts]
+    longest = 0
+    for net in range(1, 7):
+        vg.step(np.array([net] * 3, np.int32))
+        _, _, cum = vg.results_host()
+        for e, o in enumerate(orcs):
+            m = o.step(net)
+            oc, oo, ocost = o.last_paths(); gc, go, gcost = vg.paths(e)
+            assert np.array_equal(ocost, gcost) and np.array_equal(oo, go) and np.array_equal(oc, gc), (net, e)
+            assert [int(v) for v in cum[e]] == [m["violation"], m["wirelength"], m["via"], m["blocked"], m["shorted"], m["overflow"]]
+            longest = max([longest] + np.diff(oo).tolist())
+    for e, o in enumerate(orcs):
+        assert np.array_equal(vg.obs_host(e).numpy(), o.obs())
+        assert np.array_equal(vg.state(e)[0], o.state()[0])
+    rc = vg.route_counters()
+    vg.close()
+    assert longest > 300, longest
+    assert rc["window_nets"] > 0 and rc["global_nets"] == 0, rc
+
+
 def _own_walk_case():
     """Layer 0 is horizontal with x pitch 300 and y pitch 100, so an x step (300) costs exactly a y step
     (100 x (1 + GRIDCOST)).  Net 1: the walk back from (2,6,0) runs along row 6 to (5,6,0), whose only real predecessor is the
