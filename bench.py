@@ -409,7 +409,6 @@ def run_ours(args):
     alg_bytes = {
         "obs": obs_bytes,                                     # 4*(2+7n)*cells written per env-step
         "metrics": 4.0 * cells * ENVS_PER_GPU * K,            # cellinfo read, b_state = 4 B/cell
-        "route_begin": 11.0 * cells * ENVS_PER_GPU * K,       # 6 B read + 5 B written per cell
     }
     kern = {}
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0

@@ -695,8 +695,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         min_cluster = 1;
         while (min_cluster < 8 && n_route * min_cluster * 2 <= 2 * env->n_sm) min_cluster <<= 1;
     }
-    bool any_global = false;
-    int n_grp[XR_NG] = {};
+    bool any_global = false, any_win = false;
+    int n_grp[XR_NG] = {}, n_glob[XR_NG] = {};            // environments per group / of them on the full-grid path
     int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then XR_NB*XR_NG lists of N: [group][bucket]
     for (int i = 0; i < g.N; i++) {
         const int a = actions[i];
@@ -728,10 +728,10 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             for (int k = 1; k < XR_NG; k++) if (np >= env->grp_pins[k]) grp = k;
             if (bucket < 0) grp = XR_NG - 1;
             if (bucket >= 0) {
-                mode = 1;
+                mode = 1; any_win = true;
                 env->p_lists[(size_t)(2 + grp * XR_NB + bucket) * g.N + nb[grp][bucket]++] = i;
                 env->n_win_nets++;
-            } else { any_global = true; env->n_global_nets++; }
+            } else { any_global = true; env->n_global_nets++; n_glob[grp]++; }
         }
         if (a != 0) n_grp[grp]++;
         env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
@@ -754,7 +754,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     // when the groups run on their own streams -- per group, so that the heavy group, the long pole of the step,
     // starts routing as soon as its own few environments are ready
     if (!split) {
-        if (any_route) { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1); }
+        if (any_global) { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1, 0); }
         { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d, -1); }
         CK(cudaGetLastError());
     }
@@ -767,7 +767,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         env->cur_grp = grp;
         if (split) {
             CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
-            if (has) { Launch L(env, XR_K_ROUTE_BEGIN, sg); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
+            if (n_glob[grp]) { Launch L(env, XR_K_ROUTE_BEGIN, sg); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, sg>>>(env->g, env->d, grp, 0); }
             { Launch L(env, XR_K_MISC, sg); k_seed<<<g.N, 64, 0, sg>>>(env->g, env->d, grp); }
         }
         for (int b = XR_NB - 1; b >= 0; b--) {              // widest clusters first: they need a whole GPC
@@ -807,6 +807,13 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         else env->res_on_host = true;
     }
     if (need_global) {
+        // lazy prologue of the environments a window kernel handed over (they skipped k_route_begin): cost flags and
+        // distance field over the whole grid, then the sources / the tree committed so far.  Both kernels return at
+        // once for everybody else.
+        if (any_win) {
+            { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1, 1); }
+            { Launch L(env, XR_K_MISC, st); k_handover_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
+        }
         long long pumps = 0;
         const long long guard = 64ll * (g.X + g.Y + g.Z) + 4096;
         for (;;) {

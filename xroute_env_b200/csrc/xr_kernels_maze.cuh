@@ -30,10 +30,19 @@
 // ---------------------------------------------------------------- route begin
 // Freeze the per-cell cost flags of the net each environment routes this step
 // and clear its distance field.  4 cells per thread, 16-byte stores.
-__global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp) {
+// Only the full-grid path reads these two arrays: environments whose net goes to a window kernel (mode 1) skip the
+// pass -- the window kernel derives its window's flags from cellinfo / apnet itself -- and get it lazily
+// (handover = 1, followed by k_handover_seed) in the rare step in which their search escapes the window.
+__device__ __forceinline__ uint32_t cost_flags(uint32_t cellinfo, uint32_t apnet, uint32_t net) {
+    return ((cellinfo & CI_USAGE_MASK) ? CF_RS : 0u) | ((apnet != 0u && apnet != net) ? CF_FS : 0u) |
+           ((cellinfo & CI_BLOCK) ? CF_BLK : 0u);
+}
+__global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp, int handover) {
     const int env = blockIdx.y;
     const int net = d.act[2 * env + 1];
-    if (net == 0 || (grp >= 0 && d.grp[env] != grp)) return;  // grp >= 0: only this post-route group's environments
+    if (net == 0) return;
+    if (handover) { if (d.mode[env] != 1 || d.phase[env] != 1) return; }
+    else if (d.mode[env] == 1 || (grp >= 0 && d.grp[env] != grp)) return;  // grp >= 0: only this post-route group
     const size_t eoff = (size_t)env * g.cells_p;
     const int n4 = g.cells_p >> 2;
     const uint4 *ci4 = reinterpret_cast<const uint4 *>(d.cellinfo + eoff);
@@ -48,14 +57,36 @@ __global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp) {
         const uint32_t a[4] = {an.x & 0xFFFFu, an.x >> 16, an.y & 0xFFFFu, an.y >> 16};
         uint32_t packed = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t f = ((c[k] & CI_USAGE_MASK) ? CF_RS : 0u) |
-                         ((a[k] != 0u && a[k] != (uint32_t)net) ? CF_FS : 0u) |
-                         ((c[k] & CI_BLOCK) ? CF_BLK : 0u);
-            packed |= f << (8 * k);
-        }
+        for (int k = 0; k < 4; k++) packed |= cost_flags(c[k], a[k], (uint32_t)net) << (8 * k);
         f4[i] = packed;
         d4[i] = inf4;
+    }
+}
+
+// Second half of the lazy prologue of a hand-over (after k_route_begin<handover>): on the first connection the sources
+// are the access points of the source pin; later the tree is what the window kernel committed -- the cells of the
+// path record (the flags just rebuilt count the net's own wires as foreign route shapes, but only on tree cells,
+// whose flags no relaxation and no backtrace ever reads: they are entered at distance 0 or not at all).
+// grid N, block 64.
+__global__ void k_handover_seed(Geo g, Dev d) {
+    const int env = blockIdx.x;
+    const int net = d.act[2 * env + 1];
+    if (net == 0 || d.mode[env] != 1 || d.phase[env] != 1) return;
+    const size_t eoff = (size_t)env * g.cells_p;
+    if (d.first[env]) {
+        const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
+        const unsigned srcpin = d.net_srcpin[(size_t)env * (g.max_nets + 1) + net];
+        const size_t aoff = (size_t)env * g.max_aps;
+        for (int i = ns[net] + threadIdx.x; i < ns[net + 1]; i += blockDim.x)
+            if (d.ap_pin[aoff + i] == srcpin) d.dist[eoff + d.ap_cellp[aoff + i]] = 0;
+        return;
+    }
+    const int *path = d.path + (size_t)env * g.path_cap;
+    const int pn = d.path_n[env] < g.path_cap ? d.path_n[env] : g.path_cap;
+    for (int k = threadIdx.x; k < pn; k += blockDim.x) {
+        const int ci = path[k];
+        const int x = ci % g.X, y = (ci / g.X) % g.Y, z = ci / (g.X * g.Y);
+        d.cflag[eoff + ((size_t)z * g.Y + y) * g.Xp + x] = CF_TREE;       // (its cost flags are never read, see above)
     }
 }
 

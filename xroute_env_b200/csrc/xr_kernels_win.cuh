@@ -385,14 +385,15 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win(Geo g, Dev d, const int 
         c.leny[i] = (gy >= 1 && gy < g.Y) ? (uint32_t)(g.yc[gy] - g.yc[gy - 1]) : 0u;
     }
     for (int i = tid; i < n_flag_bytes; i += WIN_T) c.rowd[i] = 0;
-    // ---- load the band: flags from the frozen cflag field, dist = INF; halo rows INF
+    // ---- load the band: cost flags frozen now from the occupancy and the access-point owners, dist = INF; halo rows INF
     const size_t eoff = (size_t)env * g.cells_p;
     for (int i = tid; i < c.Z * c.HH * c.WXp; i += WIN_T) {
         const int x = i % c.WXp, ly = (i / c.WXp) % c.HH, z = i / (c.WXp * c.HH);
         uint32_t v = WINF;
         if (x < WX && ly >= 1 && ly <= c.h) {
             const int gy = wy0 + c.ry0 + ly - 1;
-            v |= ((uint32_t)d.cflag[eoff + ((size_t)z * g.Y + gy) * g.Xp + wx0 + x] & 7u) << 28;
+            const size_t gi = eoff + ((size_t)z * g.Y + gy) * g.Xp + wx0 + x;
+            v |= cost_flags(__ldg(d.cellinfo + gi), __ldg(d.apnet + gi), (uint32_t)net) << 28;
         }
         c.cell[i] = v;
     }

@@ -413,20 +413,24 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
         c.leny[i] = (gy >= 1 && gy < g.Y) ? (uint32_t)(g.yc[gy] - g.yc[gy - 1]) : 0u;
     }
     for (int i = tid; i < n_flag_bytes; i += WIN_T) c.rowd[i] = 0;
-    // ---- load both layouts: flags from the frozen cflag field, dist = INF
+    // ---- load both layouts: cost flags frozen now from the occupancy and the access-point owners, dist = INF
     const size_t eoff = (size_t)env * g.cells_p;
     for (int i = tid; i < c.Z * c.HA * c.WXp; i += WIN_T) {
         const int x = i % c.WXp, ya = (i / c.WXp) % c.HA, z = i / (c.WXp * c.HA);
         uint32_t v = WINF;
-        if (x < WX && ya < c.ha)
-            v |= ((uint32_t)d.cflag[eoff + ((size_t)z * g.Y + wy0 + rank + C * ya) * g.Xp + wx0 + x] & 7u) << 28;
+        if (x < WX && ya < c.ha) {
+            const size_t gi = eoff + ((size_t)z * g.Y + wy0 + rank + C * ya) * g.Xp + wx0 + x;
+            v |= cost_flags(__ldg(d.cellinfo + gi), __ldg(d.apnet + gi), (uint32_t)net) << 28;
+        }
         c.A[i] = v;
     }
     for (int i = tid; i < c.Z * c.WB * c.WYp; i += WIN_T) {
         const int y = i % c.WYp, xb = (i / c.WYp) % c.WB, z = i / (c.WYp * c.WB);
         uint32_t v = WINF;
-        if (y < WY && xb < c.wb)
-            v |= ((uint32_t)d.cflag[eoff + ((size_t)z * g.Y + wy0 + y) * g.Xp + wx0 + rank + C * xb] & 7u) << 28;
+        if (y < WY && xb < c.wb) {
+            const size_t gi = eoff + ((size_t)z * g.Y + wy0 + y) * g.Xp + wx0 + rank + C * xb;
+            v |= cost_flags(__ldg(d.cellinfo + gi), __ldg(d.apnet + gi), (uint32_t)net) << 28;
+        }
         c.B[i] = v;
     }
     if (tid < 8) s_flag[tid] = 0;
