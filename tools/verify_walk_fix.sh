@@ -1,5 +1,9 @@
 # A/B of the backtrace fix: the regression tests must FAIL on the library built from the previous commit
-# (tools/_ab/libxroute_b200_old.so, built by hand from `git archive`) and pass on the current one; then the fuzz
+# (tools/_ab/libxroute_b200_old.so -- build it here first, it is not kept:
+#    mkdir -p /tmp/old tools/_ab && git archive <commit before ecdee9d> xroute_env_b200/csrc include | tar -x -C /tmp/old &&
+#    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -shared -Xcompiler -fPIC \
+#         -o tools/_ab/libxroute_b200_old.so /tmp/old/xroute_env_b200/csrc/xr_api.cu)
+# and pass on the current one; then the fuzz
 # campaign that found the case, the whole GPU suite and a bench line.
 mkdir -p gpurun_out
 XROUTE_B200_LIB=$PWD/tools/_ab/libxroute_b200_old.so timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "own_walk" > gpurun_out/walk_old.log 2>&1; echo "old lib rc=$? (expected 1)"
