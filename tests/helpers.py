@@ -82,11 +82,19 @@ def brute_force_dist(geom, cflag, sources):
         d = nd
 
 
-def spec_route_net(geom, inst, usage, owner, net):
+def spec_route_net(geom, inst, usage, owner, net, goal_directed=False):
     """Second, independent restatement of SPEC steps 1-3 in plain Python on top of the dense
     Bellman-Ford above -- no code shared with oracle/xr_oracle.c: source pin, all-targets search, canonical target,
     canonical backtrace on the converged field, commit.  usage / owner [Z,Y,X] are updated in place.
-    Returns (cells, conn_off, conn_cost, d_wirelength, d_via) like OracleEnv.last_paths()."""
+    Returns (cells, conn_off, conn_cost, d_wirelength, d_via) like OracleEnv.last_paths().
+
+    goal_directed=True replaces the converged field by a PARTIAL one: best-first search on f = d + h, h = L1 track
+    distance (DBU) to the nearest unconnected access point, stopped once the smallest open f exceeds the best target
+    distance B.  Only cells with d + h <= B hold their final distance; the others keep whatever tentative value (or
+    infinity) the search left.  DESIGN.md section 12 argues that target choice and canonical walk come out the same
+    (h is consistent: cost >= 1 per DBU, vias cost > 0; every cell of a shortest path to a best target, and every
+    predecessor the walk may accept, has d + h <= B; a tentative value is never smaller than the final one, so it can
+    not fake the equality d[p] + w = d[c]); the tests hold it to that."""
     Z, Y, X = usage.shape
     xc, yc = geom.x_coords.astype(np.int64), geom.y_coords.astype(np.int64)
     aps = [(int(p), tuple(int(v) for v in xyz)) for n, p, xyz in zip(inst.ap_net, inst.ap_pin, inst.ap_xyz) if n == net]
@@ -112,15 +120,48 @@ def spec_route_net(geom, inst, usage, owner, net):
         length = abs(int(xc[cx] - xc[px])) + abs(int(yc[cy] - yc[py]))
         return length * (mult + geom.grid_cost * (axis != int(geom.layer_dir[cz]))) + pen
 
+    DELTA = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
     xs, ys = [a[1][0] for a in aps], [a[1][1] for a in aps]
     cx2, cy2 = min(xs) + max(xs), min(ys) + max(ys)
     src_pin = min((abs(2 * x - cx2) + abs(2 * y - cy2), p) for p, (x, y, z) in aps)[1]
     tree = [xyz for p, xyz in aps if p == src_pin]
     connected = {src_pin}
-    DELTA = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
     cells, off, costs, wl, via, first = [], [0], [], 0, 0, True
+    def partial_field(tree, targets):
+        import heapq
+        INF = np.int64(1) << 40
+        d = np.full((Z, Y, X), INF, np.int64)
+        txy = np.array([(int(xc[x]), int(yc[y])) for (x, y, z) in targets], np.int64)
+        hval = lambda c: int((np.abs(txy[:, 0] - int(xc[c[0]])) + np.abs(txy[:, 1] - int(yc[c[1]]))).min())
+        tset, best, heap = set(targets), INF, []
+        for c in tree:
+            d[c[2], c[1], c[0]] = 0
+            heapq.heappush(heap, (hval(c), 0, c))
+            if c in tset:
+                best = 0
+        while heap:
+            f, dc, c = heapq.heappop(heap)
+            if f > best:
+                break
+            if dc != d[c[2], c[1], c[0]]:
+                continue
+            for k in range(6):
+                v = (c[0] + DELTA[k][0], c[1] + DELTA[k][1], c[2] + DELTA[k][2])
+                if not (0 <= v[0] < X and 0 <= v[1] < Y and 0 <= v[2] < Z):
+                    continue
+                nd = dc + w(c, v)
+                if nd < d[v[2], v[1], v[0]]:
+                    d[v[2], v[1], v[0]] = nd
+                    heapq.heappush(heap, (nd + hval(v), nd, v))
+                    if v in tset and nd < best:
+                        best = nd
+        return d
+
     while len(connected) < len(pins):
-        d = brute_force_dist(geom, cflag, tree)
+        if goal_directed:
+            d = partial_field(tree, [xyz for p, xyz in aps if p not in connected])
+        else:
+            d = brute_force_dist(geom, cflag, tree)
         tgt = min((int(d[z, y, x]), (z * Y + y) * X + x, (x, y, z)) for p, (x, y, z) in aps if p not in connected)
         costs.append(tgt[0])
         c, last, path = tgt[2], None, [tgt[2]]

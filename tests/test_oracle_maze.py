@@ -195,3 +195,32 @@ def test_whole_net_routing_matches_independent_restatement(seed):
         assert (m["d_wirelength"], m["d_via"]) == (wl, via)
         ou, oown = env.state()
         assert np.array_equal(ou, usage) and np.array_equal(oown, owner)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_goal_directed_partial_field_gives_the_same_routes(seed):
+    """Ground work for a goal-directed GPU search: a best-first search on d + h that stops at the
+    best target distance B leaves only the cells with d + h <= B final (1-3 % of a window on the bench workload,
+    tools/analyze_pruning.py) -- target choice, canonical walk, commit and metrics must not change.  Tie-heavy grids,
+    obstacles and foreign wires included; counted: the share of cells the partial search left unsettled."""
+    rng = np.random.default_rng(700 + seed)
+    X, Y, Z = int(rng.integers(8, 22)), int(rng.integers(8, 22)), int(rng.integers(2, 5))
+    g = ispd18_geometry(X, Y, Z)
+    if seed % 2:
+        px, py = rng.choice([100, 200, 300], 2)
+        g.x_coords = (np.cumsum(rng.choice([1, 1, 2, 3], X)) * px).astype(np.int32)
+        g.y_coords = (py * np.arange(Y)).astype(np.int32)
+        g.layer_dir = rng.integers(0, 2, Z).astype(np.uint8)
+        g.layer_pitch = rng.choice([25, 50, 75, 100], Z).astype(np.int32)
+        g.via_cost, g.grid_cost = int(rng.choice([1, 2, 4])), int(rng.choice([0, 1, 2]))
+    inst = make_instance(g, 6, 800 + seed, p_obstacle=0.2)
+    env = OracleEnv(g, inst)
+    usage, owner = np.zeros((Z, Y, X), np.uint8), np.zeros((Z, Y, X), np.uint16)
+    for net in rng.permutation(inst.net_ids):
+        m = env.step(int(net))
+        cells, off, cost, wl, via = spec_route_net(g, inst, usage, owner, int(net), goal_directed=True)
+        oc, oo, ocost = env.last_paths()
+        assert ocost.tolist() == cost and oo.tolist() == off and oc.tolist() == cells, (seed, net)
+        assert (m["d_wirelength"], m["d_via"]) == (wl, via)
+    ou, oown = env.state()
+    assert np.array_equal(ou, usage) and np.array_equal(oown, owner)
