@@ -118,4 +118,4 @@ for delta in deltas:
             q = r[m]
             print(f"   {name:30s} n={len(q):4d}  rounds mean {q[:, 2].mean():7.1f} p90 {np.percentile(q[:, 2], 90):6.0f} max {q[:, 2].max():5d} | "
                   f"expansions mean {q[:, 3].mean():8.1f} max {q[:, 3].max():6d} | widest round mean {q[:, 4].mean():6.1f} max {q[:, 4].max():5d} | "
-                  f"cells touched mean {q[:, 6].mean():8.1f} | path cells mean {q[:, 5].mean():5.1f}")
+                  f"cells touched mean {q[:, 6].mean():8.1f} p99 {np.percentile(q[:, 6], 99):7.0f} max {q[:, 6].max():6d} | path cells mean {q[:, 5].mean():5.1f}")
