@@ -166,7 +166,8 @@ int xr_legal_mask(const XrEnv *env, int32_t env_id, uint8_t *mask, int32_t *n_re
 int xr_get_paths(XrEnv *env, int32_t env_id, int32_t *cells, int32_t cells_cap, int32_t *n_cells,
                  int32_t *conn_off, uint32_t *conn_cost, int32_t conn_cap, int32_t *n_conn);
 int xr_get_state(XrEnv *env, int32_t env_id, uint8_t *usage, uint16_t *owner);   /* [Z][Y][X] */
-int xr_get_dist(XrEnv *env, int32_t env_id, uint32_t *dist);                     /* [Z][Y][X] */
+int xr_get_dist(XrEnv *env, int32_t env_id, uint32_t *dist);                     /* [Z][Y][X]; the full-grid path's
+                                                   scratch field: meaningful only after a net routed with window_margin = -1 */
 
 /* Refresh XR_BUF_STATS from the per-environment counters (asynchronous).        */
 int xr_stats_update(XrEnv *env, void *stream);
