@@ -112,7 +112,8 @@ for delta in deltas:
             lag.step(net)
     r = np.array(rows, np.int64)
     print(f"delta {delta} DBU: {len(r)} connections, every target / cost / path == oracle")
-    for name, m in (("all", np.ones(len(r), bool)), ("first connections", r[:, 1] == 0), ("later connections", r[:, 1] > 0),
+    for name, m in (("all", np.ones(len(r), bool)), ("first connections", r[:, 1] == 0), ("first, 2-3 pin nets", (r[:, 1] == 0) & (r[:, 0] <= 3)),
+                    ("first, >= 8 pin nets", (r[:, 1] == 0) & (r[:, 0] >= 8)), ("later connections", r[:, 1] > 0),
                     (">= 8 pins, later connections", (r[:, 0] >= 8) & (r[:, 1] > 0))):
         if m.sum():
             q = r[m]
