@@ -84,7 +84,13 @@ typedef struct XrConfig {
                                   the net blocks that shift down) -- bit-identical to a rebuild, the
                                   consumer must treat the buffer as read-only;
                                   1 = full rebuild of every stepped environment's observation        */
-    int32_t reserved[4];
+    int32_t engine;            /* maze-route engine: 0 = goal-directed frontier search (default; one CTA per net on an
+                                  epoch-tagged field in global memory, no window), 1 = the sweep engines (window-resident
+                                  cluster kernels, full-grid sweeps as their fall-back).  Same results, bit for bit.   */
+    int32_t metrics_mode;      /* 0 = blocked / shorted / overflow counts are maintained by the commits (O(path cells));
+                                  1 = recomputed by a full scan of the occupancy field every step (the checker, and the
+                                  HBM-bound "reward kernel" the roofline is quoted on).  Same results.                  */
+    int32_t reserved[2];
 } XrConfig;
 
 /* cumulative metric slots of xr_step_results / XR_BUF_CUM */
@@ -113,7 +119,7 @@ enum { XR_S_STEPS = 0, XR_S_EPISODES = 1, XR_S_VIOLATION = 2, XR_S_WIRELENGTH = 
 
 /* kernel classes of xr_profile_get */
 enum { XR_K_OBS = 0, XR_K_METRICS = 1, XR_K_ROUTE_BEGIN = 2, XR_K_SWEEP_XZ = 3, XR_K_SWEEP_Y = 4,
-       XR_K_CONTROL = 5, XR_K_ROUTE_WIN = 6, XR_K_MISC = 7, XR_K_COUNT = 8 };
+       XR_K_CONTROL = 5, XR_K_ROUTE_WIN = 6, XR_K_MISC = 7, XR_K_ROUTE_FRONTIER = 8, XR_K_COUNT = 9 };
 
 int  xr_version(void);
 int  xr_create(const XrConfig *cfg, XrEnv **out);
@@ -179,9 +185,15 @@ int xr_counters(const XrEnv *env, int64_t *kernel_launches, int64_t *relax_passe
 /* Route-path usage since creation: nets routed by the window kernel, nets that started
  * on the full-grid path, and window searches handed over to it (exit test failed).  */
 int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *global_nets, int64_t *window_fallbacks);
+/* Nets routed by the frontier engine (XrConfig.engine 0) since creation, and the relaxation rounds they took. */
+int xr_frontier_counters(XrEnv *env, int64_t *frontier_nets, int64_t *rounds);
 /* Window-kernel diagnostics, uint64 [16] ([8..14] per-phase cycles when built with -DWIN_PHASE_TIMING): iterations, connections, relax cycles, kernel
  * cycles (rank-0 CTAs), nets, sum of window areas (cells per layer).                  */
 int xr_debug_counters(XrEnv *env, uint64_t *out);
+/* Per-environment record of the last frontier launch, uint64 [N][8] (meaningful when the library was built with
+ * -DFR_TIMING): cycles, rounds, expanded entries, connections, expand cycles, classify cycles, access points,
+ * largest open list.                                                                     */
+int xr_debug_env_records(XrEnv *env, uint64_t *out);
 /* Profiling timeline, double [9]: per post-route group (3) mean ms offsets from step start of
  * route start, route end, observation end (needs xr_profile_enable).                 */
 int xr_debug_timeline(XrEnv *env, double *out);

@@ -59,7 +59,7 @@ def _check_full(preset, n_envs, n_nets, sample, seed, gen_kw=None, obs_cap=-1):
 
 def test_config2_syn256_64_envs_full_episode():
     rc = _check_full("SYN-256", 64, 32, sample=(0, 21, 42, 63), seed=20260000)
-    assert rc["window_nets"] == 64 * 32 and rc["global_nets"] == 0
+    assert rc["frontier_nets"] == 64 * 32 and rc["global_nets"] == 0 and rc["window_nets"] == 0
 
 
 def test_config3_t1_7x7_shard_512_envs_full_episode():
@@ -70,7 +70,8 @@ def test_config5_t1_1x1_shard_1024_envs_full_episode():
     _check_full("T1-1x1", 1024, 32, sample=(0, 7, 1023), seed=32, gen_kw={"max_degree": 6})
 
 
-def test_config4_syn1024_congested_nets_on_and_off_chip():
+@pytest.mark.parametrize("engine", [0, 1], ids=["frontier", "sweeps"])
+def test_config4_syn1024_congested_nets_on_and_off_chip(engine):
     """1024x1024x9, 128 nets clustered around hot spots (observation materialised for the first 8 nets only):
     windows up to 540x540 do not fit a cluster's shared memory, so this exercises the 16-CTA bucket and the
     full-grid HBM sweeps next to the on-chip kernels -- all bit-exact against the oracle."""
@@ -78,7 +79,7 @@ def test_config4_syn1024_congested_nets_on_and_off_chip():
     from xroute_env_b200 import VecGame
     geom = preset_geometry("SYN-1024")
     insts = make_batch(geom, 2, 128, 777, hot_spots=16, hot_sigma=32.0)
-    vg = VecGame(geom, insts, device=0, obs_max_nets=8)
+    vg = VecGame(geom, insts, device=0, obs_max_nets=8, engine=engine)
     vg.reset()
     oracles = [OracleEnv(geom, i) for i in insts]
     # pick nets of very different extents: the largest and the smallest windows of each environment first
@@ -100,5 +101,8 @@ def test_config4_syn1024_congested_nets_on_and_off_chip():
             oc, oo, ocost = orc.last_paths(); gc, go, gcost = vg.paths(e)
             assert np.array_equal(oc, gc) and np.array_equal(ocost, gcost), (t, e)
     rc = vg.route_counters()
-    assert rc["global_nets"] >= 1 and rc["window_nets"] >= 1, rc
+    if engine == 1:
+        assert rc["global_nets"] >= 1 and rc["window_nets"] >= 1, rc
+    else:
+        assert rc["frontier_nets"] == 12 and rc["global_nets"] == 0, rc
     vg.close()

@@ -68,7 +68,37 @@ def test_route_paths_agree_across_engines(kw):
     full-grid path alone must all reproduce the oracle bit-exactly."""
     geom = ispd18_geometry(48, 44, 9)
     insts = make_batch(geom, 5, 10, seed=900, p_obstacle=0.2)
-    _run_episode(geom, insts, seed=8, **kw)
+    _run_episode(geom, insts, seed=8, engine=1, **kw)
+
+
+@pytest.mark.parametrize("knobs", [{}, {"XR_FR_RAY": "1"}, {"XR_FR_RAY": "3", "XR_FR_DELTA": "0"}, {"XR_FR_DELTA": "400"},
+                                   {"XR_FR_DELTA": "1000000"}, {"XR_FR_CAP": "64"}, {"XR_FR_THREADS": "64", "XR_FR_CAP": "128"},
+                                   {"XR_FR_THREADS": "128", "XR_FR_RAY": "5"}],
+                         ids=["default", "ray1", "ray3-delta0", "delta400", "delta-inf", "spill", "t64-spill", "t128-ray5"])
+def test_frontier_engine_knobs(knobs, monkeypatch):
+    """The default engine (goal-directed frontier search, csrc/xr_frontier.cu) for every ray length, bucket width,
+    block size and with open lists that spill to global memory: the knobs change the schedule of the relaxations,
+    never a distance the target choice or the walk reads -- paths, costs, metrics and observations stay bit-exact.
+    metrics_mode 1 on top checks the commit-maintained congestion counts against the full scan."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    geom = ispd18_geometry(48, 44, 9)
+    insts = make_batch(geom, 5, 10, seed=900, p_obstacle=0.2)
+    _run_episode(geom, insts, seed=8)
+    _run_episode(geom, insts[:2], seed=9, metrics_mode=1)
+    geom = ispd18_geometry(90, 70, 9)
+    geom.x_coords = np.cumsum(np.random.default_rng(1).integers(100, 700, 90)).astype(np.int32)   # non-uniform pitch
+    _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, check_obs_every=4)
+
+
+@pytest.mark.parametrize("engine", [0, 1], ids=["frontier", "sweeps"])
+def test_metrics_by_scan_and_by_commit_agree(engine):
+    """Congested instance (shorts, blocked cells, overflow all non-zero): the counts the commits maintain
+    (metrics_mode 0) and the per-step scan of the occupancy field (metrics_mode 1) both equal the oracle's."""
+    geom = ispd18_geometry(30, 30, 3)
+    insts = make_batch(geom, 4, 24, seed=41, p_obstacle=0.35)
+    for mm in (0, 1):
+        _run_episode(geom, insts, seed=6, engine=engine, metrics_mode=mm, check_obs_every=6)
 
 
 @pytest.mark.parametrize("obs_mode", [0, 1], ids=["incremental", "full-rebuild"])
@@ -115,11 +145,11 @@ def test_dual_cyclic_layout_kernel(minc, cluster, monkeypatch):
     monkeypatch.setenv("XR_DUAL_MINC", str(minc))
     geom = ispd18_geometry(48, 44, 9)
     insts = make_batch(geom, 5, 10, seed=900, p_obstacle=0.2)
-    _run_episode(geom, insts, seed=8, min_cluster=cluster)
-    _run_episode(geom, insts[:2], seed=9, min_cluster=cluster, window_margin=1)
+    _run_episode(geom, insts, seed=8, min_cluster=cluster, engine=1)
+    _run_episode(geom, insts[:2], seed=9, min_cluster=cluster, window_margin=1, engine=1)
     geom = ispd18_geometry(90, 70, 9)
     geom.x_coords = np.cumsum(np.random.default_rng(1).integers(100, 700, 90)).astype(np.int32)   # non-uniform pitch
-    _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, min_cluster=cluster, check_obs_every=4)
+    _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, min_cluster=cluster, check_obs_every=4, engine=1)
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -141,8 +171,9 @@ def test_tie_heavy_grids(seed, monkeypatch):
     if seed % 2:
         monkeypatch.setenv("XR_DUAL_PINS", "2"); monkeypatch.setenv("XR_DUAL_MINC", "2")
     insts = make_batch(geom, 4, 8, seed=510 + seed, p_obstacle=0.25)
-    _run_episode(geom, insts, seed=seed, min_cluster=2 if seed < 2 else 0, check_obs_every=3)
-    _run_episode(geom, insts[:2], seed=seed, window_margin=-1, check_obs_every=8)
+    _run_episode(geom, insts, seed=seed, check_obs_every=3)                                        # frontier engine
+    _run_episode(geom, insts, seed=seed, min_cluster=2 if seed < 2 else 0, check_obs_every=3, engine=1)
+    _run_episode(geom, insts[:2], seed=seed, window_margin=-1, check_obs_every=8, engine=1)
 
 
 def _strip_instances():
@@ -166,7 +197,7 @@ def _strip_instances():
     return geom, insts
 
 
-@pytest.mark.parametrize("engine", ["band", "dual"])
+@pytest.mark.parametrize("engine", ["band", "dual", "frontier"])
 def test_long_paths_span_several_commit_flushes(engine, monkeypatch):
     """A 700-track-wide strip: single connections of several hundred cells.  The window kernels stage at most 256 path
     cells on chip before a parallel commit pass, and put the whole walk on the tree from the path record afterwards --
@@ -176,7 +207,7 @@ def test_long_paths_span_several_commit_flushes(engine, monkeypatch):
     if engine == "dual":
         monkeypatch.setenv("XR_DUAL_PINS", "2"); monkeypatch.setenv("XR_DUAL_MINC", "2")
     geom, insts = _strip_instances()
-    vg = VecGame(geom, insts, device=0, min_cluster=2)
+    vg = VecGame(geom, insts, device=0, min_cluster=2, engine=0 if engine == "frontier" else 1)
     vg.reset()
     orcs = [OracleEnv(geom, i) for i in insts]
     longest = 0
@@ -195,7 +226,8 @@ def test_long_paths_span_several_commit_flushes(engine, monkeypatch):
     rc = vg.route_counters()
     vg.close()
     assert longest > 300, longest
-    assert rc["window_nets"] > 0 and rc["global_nets"] == 0, rc
+    if engine != "frontier":
+        assert rc["window_nets"] > 0 and rc["global_nets"] == 0, rc
 
 
 def _own_walk_case():
@@ -216,7 +248,7 @@ def _own_walk_case():
     return geom, inst
 
 
-@pytest.mark.parametrize("engine", ["band", "dual", "global"])
+@pytest.mark.parametrize("engine", ["band", "dual", "global", "frontier"])
 def test_backtrace_ignores_the_cells_of_its_own_walk(engine, monkeypatch):
     """Found by tools/fuzz_parity.py (non-uniform grid, configuration 762 of seed 7): every engine used to turn the
     cells of a walk into sources (distance 0) while still walking, and a later cell of the same walk could then accept
@@ -229,7 +261,7 @@ def test_backtrace_ignores_the_cells_of_its_own_walk(engine, monkeypatch):
         monkeypatch.setenv("XR_DUAL_PINS", "2"); monkeypatch.setenv("XR_DUAL_MINC", "2")
     if engine == "global":
         kw = dict(window_margin=-1)
-    vg = VecGame(geom, [inst], device=0, **kw)
+    vg = VecGame(geom, [inst], device=0, engine=0 if engine == "frontier" else 1, **kw)
     vg.reset()
     orc = OracleEnv(geom, inst)
     for net in (1, 2, 3):
@@ -262,8 +294,8 @@ def test_window_fallback_counter_and_exactness():
     from xroute_env_b200 import VecGame
     geom = ispd18_geometry(64, 64, 9)
     insts = make_batch(geom, 4, 12, seed=910, p_obstacle=0.3)
-    _run_episode(geom, insts, seed=9, window_margin=1)
-    vg = VecGame(geom, insts, device=0, window_margin=1)
+    _run_episode(geom, insts, seed=9, window_margin=1, engine=1)
+    vg = VecGame(geom, insts, device=0, window_margin=1, engine=1)
     vg.reset()
     for net in (1, 2, 3, 4, 5, 6):
         vg.step(np.array([net] * 4, np.int32))

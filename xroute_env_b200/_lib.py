@@ -16,10 +16,10 @@ XR_OK = 0
 XR_E_INVALID, XR_E_CUDA, XR_E_ILLEGAL, XR_E_CAPACITY, XR_E_UNROUTABLE, XR_E_STATE = -1, -2, -3, -4, -5, -6
 XR_M_COUNT = 6
 XR_STATS_COUNT = 16
-XR_K_COUNT = 8
+XR_K_COUNT = 9
 (XR_BUF_OBS, XR_BUF_DELTA, XR_BUF_CUM, XR_BUF_DONE, XR_BUF_NREMAIN, XR_BUF_LEGAL, XR_BUF_STATS,
  XR_BUF_REWARD, XR_BUF_NETFEAT) = range(9)
-K_NAMES = ["obs", "metrics", "route_begin", "sweep_xz", "sweep_y", "control", "route_win", "misc"]
+K_NAMES = ["obs", "metrics", "route_begin", "sweep_xz", "sweep_y", "control", "route_win", "misc", "route_frontier"]
 STAT_NAMES = ["steps", "episodes", "violation", "wirelength", "via", "blocked", "shorted", "overflow",
               "reward_x2", "relax_passes", "cells_relaxed", "connections"]
 
@@ -36,7 +36,7 @@ class XrConfig(C.Structure):
         ("via_cost", C.c_int32), ("grid_cost", C.c_int32), ("drc_cost", C.c_int32),
         ("fixed_shape_cost", C.c_int32), ("block_cost", C.c_int32),
         ("pumps_per_sync", C.c_int32), ("window_margin", C.c_int32), ("min_cluster", C.c_int32),
-        ("obs_mode", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("obs_mode", C.c_int32), ("engine", C.c_int32), ("metrics_mode", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -57,6 +57,7 @@ SYMBOLS = [
     "xr_obs_dlpack", "xr_buffer_dlpack", "xr_buffer_ptr", "xr_legal_mask", "xr_get_paths",
     "xr_get_state", "xr_get_dist", "xr_stats_update", "xr_counters", "xr_profile_enable",
     "xr_profile_get", "xr_build_obs_from_nodes", "xr_route_counters", "xr_debug_counters", "xr_debug_timeline", "xr_kernel_bench",
+    "xr_frontier_counters", "xr_debug_env_records",
 ]
 
 _lib = None
@@ -115,6 +116,10 @@ def load():
     L.xr_counters.argtypes = [vp, i64p, i64p, i64p, i64p]
     L.xr_route_counters.restype = C.c_int
     L.xr_route_counters.argtypes = [vp, i64p, i64p, i64p]
+    L.xr_debug_env_records.restype = C.c_int
+    L.xr_debug_env_records.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.xr_frontier_counters.restype = C.c_int
+    L.xr_frontier_counters.argtypes = [vp, i64p, i64p]
     L.xr_kernel_bench.restype = C.c_int
     L.xr_kernel_bench.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     L.xr_debug_timeline.restype = C.c_int

@@ -1,4 +1,7 @@
-"""Build libxroute_b200.so in-tree with nvcc for sm_100a (python -m xroute_env_b200.build)."""
+"""Build libxroute_b200.so in-tree with nvcc for sm_100a (python -m xroute_env_b200.build).
+
+Two translation units (the C ABI + sweep engines, and the frontier engine) are compiled side by side into
+csrc/_obj/*.o and linked into one shared library; a unit is rebuilt only when one of its sources is newer."""
 from __future__ import annotations
 
 import os
@@ -6,22 +9,44 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "xr_api.cu")
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+UNITS = ["xr_api.cu", "xr_frontier.cu"]
 OUT = os.path.join(HERE, "libxroute_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + \
-       [os.path.join(HERE, "..", "include", "xroute_b200.h")]
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + \
+           [os.path.join(HERE, "..", "include", "xroute_b200.h")]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    cmd[1:1] = os.environ.get("XR_NVCC_EXTRA", "").split()      # e.g. -DWIN_PHASE_TIMING for tools/diag_route.py
-    subprocess.check_call(cmd)
+    extra = os.environ.get("XR_NVCC_EXTRA", "").split()      # e.g. -DWIN_PHASE_TIMING for tools/diag_route.py
+    os.makedirs(OBJ, exist_ok=True)
+    newest = max(os.path.getmtime(d) for d in _deps())
+    tag = os.path.join(OBJ, "flags.txt")
+    flags = " ".join(extra)
+    if not os.path.exists(tag) or open(tag).read() != flags:
+        force = True
+    procs, objs = [], []
+    for u in UNITS:
+        o = os.path.join(OBJ, u.replace(".cu", ".o"))
+        objs.append(o)
+        if not force and os.path.exists(o) and os.path.getmtime(o) >= newest:
+            continue
+        cmd = [nvcc] + extra + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                                "-Xcompiler", "-fPIC", "-c", "-o", o, os.path.join(CSRC, u)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((u, subprocess.Popen(cmd)))
+    failed = [u for u, p in procs if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, f"nvcc {failed}")
+    if procs or force or not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(o) for o in objs):
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs)
+    with open(tag, "w") as f:
+        f.write(flags)
     return OUT
 
 

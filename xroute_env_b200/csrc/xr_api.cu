@@ -12,6 +12,7 @@
 #include "xr_kernels_maze.cuh"
 #include "xr_kernels_win.cuh"
 #include "xr_kernels_win2.cuh"
+#include "xr_frontier.h"
 
 #include <algorithm>
 #include <atomic>
@@ -63,7 +64,12 @@ struct XrEnv {
     int heavy_cluster = 8;              // minimum cluster size of the heaviest group (0 = same as the others)
     int dual_pins = 8;                  // nets with at least this many pins use the dual cyclic layout (0 = never)
     int dual_minc = 8;                  // ... on clusters of at least this many CTAs
-    long long n_win_nets = 0, n_global_nets = 0;
+    long long n_win_nets = 0, n_global_nets = 0, n_frontier_nets = 0;
+    // frontier engine (default): one CTA per net, goal-directed search on the epoch-tagged global field
+    int engine = 0;                     // 0 = frontier, 1 = window kernels + full-grid sweeps (round-1 engines)
+    FrParams fr_big = {}, fr_small = {};// list capacities for "one CTA per SM" and "several CTAs per SM" launches
+    int fr_threads_big = FR_T, fr_threads_small = 256;
+    int metrics_mode = 0;               // 0 = congestion counts maintained by the commits, 1 = full scan (k_metrics) every step
     // counters
     long long n_launch = 0, n_sync = 0;
     // profiling
@@ -129,10 +135,10 @@ static void prof_collect(XrEnv *env) {
         float ms = 0.f;
         cudaEventSynchronize(p.b);
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { env->prof_ms[p.cls] += ms; env->prof_n[p.cls]++; }
-        if (p.step && p.grp >= 0 && p.grp < XR_NG && (p.cls == XR_K_ROUTE_WIN || p.cls == XR_K_OBS)) {
+        if (p.step && p.grp >= 0 && p.grp < XR_NG && (p.cls == XR_K_ROUTE_WIN || p.cls == XR_K_ROUTE_FRONTIER || p.cls == XR_K_OBS)) {
             float o0 = 0.f, o1 = 0.f;
             if (cudaEventElapsedTime(&o0, p.step, p.a) == cudaSuccess && cudaEventElapsedTime(&o1, p.step, p.b) == cudaSuccess) {
-                if (p.cls == XR_K_ROUTE_WIN) {
+                if (p.cls != XR_K_OBS) {
                     env->tl_sum[p.grp][0] += o0; env->tl_n[p.grp][0]++;
                     env->tl_sum[p.grp][1] += o1; env->tl_n[p.grp][1]++;
                 } else { env->tl_sum[p.grp][2] += o1; env->tl_n[p.grp][2]++; }
@@ -274,7 +280,23 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.path, N * g.path_cap); DA(d.path_n, N); DA(d.conn_off, N * (g.conn_cap + 1));
     DA(d.conn_cost, N * g.conn_cap); DA(d.conn_n, N);
     DA(env->d_ids, N);
-    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.fin, N); DA(d.dbg, 16); DA(d.netfeat, N * (g.max_nets + 1) * XR_NF);
+    {   // frontier engine: epoch-tagged distance field (all ones = older than any epoch), list spill space
+        const int cp = g.cells_p;
+        env->fr_big.cap_s = 6144; env->fr_big.cap_e = 4096;
+        env->fr_small.cap_s = 2048; env->fr_small.cap_e = 1024;
+        env->fr_big.delta = env->fr_small.delta = 1200u; env->fr_big.ray = env->fr_small.ray = FR_RAY;
+        if (const char *e = getenv("XR_FR_DELTA")) env->fr_big.delta = env->fr_small.delta = (uint32_t)std::max(0, atoi(e));
+        if (const char *e = getenv("XR_FR_RAY")) env->fr_big.ray = env->fr_small.ray = std::min(FR_RAY, std::max(1, atoi(e)));
+        if (const char *e = getenv("XR_FR_THREADS")) env->fr_threads_big = env->fr_threads_small = std::min(FR_T, std::max(64, atoi(e) / 32 * 32));
+        if (const char *e = getenv("XR_FR_CAP")) { env->fr_big.cap_s = env->fr_small.cap_s = std::max(64, atoi(e)); env->fr_big.cap_e = env->fr_small.cap_e = std::max(64, atoi(e) / 2); }
+        const int cap_g = std::max(cp / 4, 32768), cap_ge = std::max(cp / 8, 16384);
+        env->fr_big.cap_g = env->fr_small.cap_g = cap_g; env->fr_big.cap_ge = env->fr_small.cap_ge = cap_ge;
+        DA(d.dist64, N * g.cells_p);
+        ce = cudaMemset(d.dist64, 0xFF, sizeof(unsigned long long) * N * g.cells_p);
+        if (ce != cudaSuccess) { std::string m = std::string("cudaMemset dist64: ") + cudaGetErrorString(ce); xr_free(env); return fail(nullptr, XR_E_CUDA, m); }
+        DA(d.fr_epoch, N); DA(d.fr_spill, N * xr_frontier_spill_words(env->fr_big)); DA(d.minc, N * 4);
+    }
+    DA(d.net_win, N * (g.max_nets + 1) * 6); DA(d.fin, N); DA(d.dbg, 16 + N * 8); DA(d.netfeat, N * (g.max_nets + 1) * XR_NF);
     {   // the observation block is the big one: do not memset it twice, but report OOM clearly
         void *q = nullptr;
         ce = cudaMalloc(&q, sizeof(float) * N * (size_t)g.obs_stride);
@@ -332,6 +354,12 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
+    env->engine = cfg->engine == 1 ? 1 : 0;
+    if (const char *e = getenv("XR_ENGINE")) env->engine = atoi(e) == 1 ? 1 : 0;
+    env->metrics_mode = cfg->metrics_mode == 1 ? 1 : 0;
+    if (const char *e = getenv("XR_METRICS_MODE")) env->metrics_mode = atoi(e) == 1 ? 1 : 0;
+    ce = xr_frontier_init(env->smem_cap);
+    if (ce != cudaSuccess) { std::string m = std::string("frontier kernel attribute: ") + cudaGetErrorString(ce); xr_free(env); return fail(nullptr, XR_E_CUDA, m); }
     // tuning knobs (not part of the ABI): XR_HEAVY_PINS, XR_HEAVY_CLUSTER
     if (const char *e = getenv("XR_MEDIUM_PINS")) env->grp_pins[1] = std::max(2, atoi(e));
     if (const char *e = getenv("XR_HEAVY_PINS")) env->grp_pins[2] = std::max(env->grp_pins[1], atoi(e));
@@ -696,6 +724,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         while (min_cluster < 8 && n_route * min_cluster * 2 <= 2 * env->n_sm) min_cluster <<= 1;
     }
     bool any_global = false, any_win = false;
+    std::vector<long long> fr_order;                      // frontier engine: (pin-count key, env), sorted before the upload
     int n_grp[XR_NG] = {}, n_glob[XR_NG] = {};            // environments per group / of them on the full-grid path
     int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then XR_NB*XR_NG lists of N: [group][bucket]
     for (int i = 0; i < g.N; i++) {
@@ -708,6 +737,14 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             const int WY = env->h_netwin[((size_t)i * (g.max_nets + 1) + a) * 2 + 1];
             int bucket = -1;
             const int mc = (np >= env->grp_pins[XR_NG - 1] && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
+            if (env->engine == 0 && env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= FR_MAXAP && np <= FR_MAXPIN) {
+                // frontier engine: one CTA per net, no window; every such environment is finalised by one epilogue
+                fr_order.push_back(((long long)(65535 - std::min(np, 65535)) << 32) | (unsigned)i);   // many-pin nets first
+                env->n_frontier_nets++;
+                env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
+                modes[i] = 2; grps[i] = 0; n_grp[0]++;
+                continue;
+            }
             if (WX > 0 && env->dual_pins > 0 && np >= env->dual_pins && WX < 1024 && WY < 1024 &&
                 env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= WIN_TGT_CAP) {
                 for (int b = NB_BAND; b < XR_NB && bucket < 0; b++) {
@@ -737,7 +774,12 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
         modes[i] = mode; grps[i] = grp;
     }
-    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * (size_t)(any_route ? 4 + XR_NB * XR_NG : 4) * g.N,
+    const int n_fr = (int)fr_order.size();
+    if (n_fr) {                                           // the frontier list rides in the (group 0, bucket 0) slot
+        std::sort(fr_order.begin(), fr_order.end());
+        for (int k = 0; k < n_fr; k++) env->p_lists[(size_t)2 * g.N + k] = (int32_t)(fr_order[k] & 0xFFFFFFFFll);
+    }
+    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * (size_t)(any_route ? (any_win || any_global ? 4 + XR_NB * XR_NG : 5) : 4) * g.N,
                        cudaMemcpyHostToDevice, st));       // act | mode | grp | env lists in one copy
     // ---- the two post-route groups run on their own streams: the light group's metric and
     // observation kernels (HBM bound) overlap the heavy group's on-chip routing
@@ -770,13 +812,20 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (n_glob[grp]) { Launch L(env, XR_K_ROUTE_BEGIN, sg); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, sg>>>(env->g, env->d, grp, 0); }
             { Launch L(env, XR_K_MISC, sg); k_seed<<<g.N, 64, 0, sg>>>(env->g, env->d, grp); }
         }
+        if (grp == 0 && n_fr) {
+            const bool big = n_fr <= env->n_sm;
+            Launch L(env, XR_K_ROUTE_FRONTIER, sg);
+            cudaError_t e = xr_frontier_launch(env->g, env->d, env->d_lists, n_fr, big ? env->fr_big : env->fr_small,
+                                               big ? env->fr_threads_big : env->fr_threads_small, sg);
+            if (e != cudaSuccess) { env->err = std::string("k_route_frontier launch: ") + cudaGetErrorString(e); return XR_E_CUDA; }
+        }
         for (int b = XR_NB - 1; b >= 0; b--) {              // widest clusters first: they need a whole GPC
             if (!nb[grp][b]) continue;
             int rc = launch_route_win(env, sg, CS[b], b >= NB_BAND, nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);
             if (rc != XR_OK) return rc;
         }
-        if (has) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
-        { Launch L(env, XR_K_MISC, sg); k_finalize<<<(g.N + 127) / 128, 128, 0, sg>>>(env->g, env->d, grp); }
+        if (has && env->metrics_mode == 1) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }
+        { Launch L(env, XR_K_MISC, sg); k_finalize<<<(g.N + 127) / 128, 128, 0, sg>>>(env->g, env->d, grp, env->metrics_mode == 0); }
         if (has) {
             Launch L(env, XR_K_OBS, sg);
             if (env->obs_mode == 1) {
@@ -834,8 +883,8 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (env->p_flags[0] == 0) break;
             if (pumps > guard * 64) return fail(env, XR_E_UNROUTABLE, "maze search did not converge");
         }
-        { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -1); }
-        { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -1); }
+        if (env->metrics_mode == 1) { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -1); }
+        { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -1, env->metrics_mode == 0); }
         {
             int maxn = 0;
             for (int k = 0; k < XR_NG; k++) maxn = std::max(maxn, maxn_grp[k]);
@@ -1091,6 +1140,18 @@ extern "C" int xr_route_counters(XrEnv *env, int64_t *window_nets, int64_t *glob
     return XR_OK;
 }
 
+extern "C" int xr_frontier_counters(XrEnv *env, int64_t *frontier_nets, int64_t *rounds) {
+    if (!env) return XR_E_INVALID;
+    if (frontier_nets) *frontier_nets = env->n_frontier_nets;
+    if (rounds) {                       // (relaxation rounds of the frontier engine = relax_passes of xr_counters)
+        int64_t p = 0;
+        int rc = xr_counters(env, nullptr, &p, nullptr, nullptr);
+        if (rc != XR_OK) return rc;
+        *rounds = p;
+    }
+    return XR_OK;
+}
+
 /* Stand-alone timing of one HBM-bound kernel over ALL environments of the handle (for the
  * roofline: inside a step these kernels overlap the routing of other groups).  which:
  * XR_K_OBS (rebuilds every observation in place, state unchanged) or XR_K_METRICS
@@ -1166,6 +1227,15 @@ extern "C" int xr_debug_counters(XrEnv *env, uint64_t *out) {
     cudaSetDevice(env->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, env->d.dbg, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+    return XR_OK;
+}
+/* Per-environment record of the last frontier launch (kernel built with -DFR_TIMING): uint64 [N][8] = cycles, rounds,
+ * expanded entries, connections, expand cycles, classify cycles, access points, largest open list. */
+extern "C" int xr_debug_env_records(XrEnv *env, uint64_t *out) {
+    if (!env || !out) return XR_E_INVALID;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, env->d.dbg + 16, sizeof(uint64_t) * 8 * env->g.N, cudaMemcpyDeviceToHost));
     return XR_OK;
 }
 

@@ -29,6 +29,24 @@
 #define CF_BLK  4u   // blockage
 #define CF_TREE 8u   // cell belongs to the tree of the net being routed
 
+// Frontier cell word (64 bit, one per cell): everything a relaxation needs in ONE load.
+//   [63:34] ~epoch (30 bits)  a word of an older epoch reads as distance = infinity; all ones = older than any epoch
+//   [33:4]  distance (30 bits, XR_INF = all ones)
+//   [3] access point of the net being routed (set by the frontier kernel for the duration of the net)
+//   [2] access point of some net   [1] blockage   [0] a committed wire covers the cell
+// atomicMin on the whole word relaxes the cell (newer epoch and smaller distance both compare smaller; the flag bits of
+// a cell are the same in every candidate value).
+#define FRW_RS  1ull
+#define FRW_BLK 2ull
+#define FRW_AP  4ull
+#define FRW_OWN 8ull
+#define FRW_FLAGS 15ull
+#define FRW_STALE 0xFFFFFFFFFFFFFFF0ull
+#define FRW_EPOCH_MASK 0x3FFFFFFFu
+__host__ __device__ inline unsigned long long frw_make(uint32_t hi30, uint32_t dist, uint32_t flags) {
+    return ((unsigned long long)hi30 << 34) | ((unsigned long long)dist << 4) | flags;
+}
+
 struct Geo {
     int N, X, Y, Z, Xp;
     int cells;        // X*Y*Z
@@ -96,6 +114,11 @@ struct Dev {
     uint8_t  *obs_do;     // [N]
     uint8_t  *obs_full;   // [N] reset: 1 = full observation build, 0 = incremental (buffer invariant holds)
     float    *obs;        // [N][obs_stride]
+    // frontier engine (xr_frontier.cu): sparse goal-directed search on an epoch-tagged field
+    unsigned long long *dist64;   // [N][cells_p]  frontier cell word, see FRW_* below
+    uint32_t *fr_epoch;           // [N] epoch of the last connection searched
+    uint32_t *fr_spill;           // [N][4*cap_g + 2*cap_ge] open-list / expansion-list entries beyond the shared-memory part
+    long long *minc;              // [N][4] blocked, shorted, overflow maintained by the commits (checked against k_metrics)
     // last routed paths (parity / debug)
     int32_t  *path;       // [N][path_cap] canonical indices
     int32_t  *path_n;     // [N]
@@ -116,4 +139,25 @@ __device__ __forceinline__ uint32_t wgt_y(const Geo &g, int z, uint32_t len, uin
 // via between layers zl and zl+1 entering layer zv
 __device__ __forceinline__ uint32_t wgt_v(const Geo &g, int zl, int zv, uint32_t f) {
     return g.vlen[zl] * g.multV[f & 3u] + ((f & CF_BLK) ? g.pen[zv] : 0u);
+}
+
+// cost flags of a cell for the net being routed, frozen from the occupancy and the access-point owner
+__device__ __forceinline__ uint32_t cost_flags(uint32_t cellinfo, uint32_t apnet, uint32_t net) {
+    return ((cellinfo & CI_USAGE_MASK) ? CF_RS : 0u) | ((apnet != 0u && apnet != net) ? CF_FS : 0u) |
+           ((cellinfo & CI_BLOCK) ? CF_BLK : 0u);
+}
+
+__device__ __forceinline__ void dir_delta(int dir, int &ddx, int &ddy, int &ddz) {
+    ddx = (dir == 0) - (dir == 1); ddy = (dir == 2) - (dir == 3); ddz = (dir == 4) - (dir == 5);
+}
+// weight of the move p -> c = p + delta(dir), f = flags of c (the cell entered)
+__device__ __forceinline__ uint32_t move_w(const Geo &g, int px, int py, int pz, int dir, uint32_t f) {
+    switch (dir) {
+    case 0: return wgt_x(g, pz, (uint32_t)(g.xc[px + 1] - g.xc[px]), f);
+    case 1: return wgt_x(g, pz, (uint32_t)(g.xc[px] - g.xc[px - 1]), f);
+    case 2: return wgt_y(g, pz, (uint32_t)(g.yc[py + 1] - g.yc[py]), f);
+    case 3: return wgt_y(g, pz, (uint32_t)(g.yc[py] - g.yc[py - 1]), f);
+    case 4: return wgt_v(g, pz, pz + 1, f);
+    default: return wgt_v(g, pz - 1, pz - 1, f);
+    }
 }

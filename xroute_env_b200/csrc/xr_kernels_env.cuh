@@ -240,7 +240,7 @@ __device__ void refresh_remaining(const Geo &g, const Dev &d, int env) {
 
 // Per-step epilogue (baseline_utils.py:426-438): metric deltas, done flag, reward
 // (train_PPO.py:101-102), remaining-net list for the order channel.
-__global__ void k_finalize(Geo g, Dev d, int pass) {
+__global__ void k_finalize(Geo g, Dev d, int pass, int use_minc) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= g.N || !pass_selects(d, env, pass)) return;
     d.fin[env] = pass_tag(pass);
@@ -251,7 +251,10 @@ __global__ void k_finalize(Geo g, Dev d, int pass) {
         return;
     }
     long long *cum = d.cum + 6 * (size_t)env;
-    const long long blocked = d.msum[4 * env], shorted = d.msum[4 * env + 1], overflow = d.msum[4 * env + 2];
+    // congestion counts: the sums of this step's scan (k_metrics), or the counts the commits maintain
+    const long long blocked = use_minc ? d.minc[4 * env] : (long long)d.msum[4 * env];
+    const long long shorted = use_minc ? d.minc[4 * env + 1] : (long long)d.msum[4 * env + 1];
+    const long long overflow = use_minc ? d.minc[4 * env + 2] : (long long)d.msum[4 * env + 2];
     d.msum[4 * env] = 0; d.msum[4 * env + 1] = 0; d.msum[4 * env + 2] = 0;
     const long long vio = blocked + shorted, wl = d.wlvia[2 * env], via = d.wlvia[2 * env + 1];
     const long long dv = vio - cum[0], dw = wl - cum[1], da = via - cum[2];
@@ -282,8 +285,12 @@ __global__ void __launch_bounds__(256) k_reset_cells(Geo g, Dev d) {
     if (!d.obs_do[env]) return;
     const size_t eoff = (size_t)env * g.cells_p;
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.cells_p; i += stride)
-        d.cellinfo[eoff + i] &= CI_STATIC_MASK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.cells_p; i += stride) {
+        const uint32_t ci = d.cellinfo[eoff + i] & CI_STATIC_MASK;
+        d.cellinfo[eoff + i] = ci;
+        // frontier cell word: no wire, stale distance, the static flags
+        d.dist64[eoff + i] = FRW_STALE | ((ci & CI_BLOCK) ? FRW_BLK : 0ull) | ((ci & CI_ISAP) ? FRW_AP : 0ull);
+    }
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < g.cells; o += stride) {
         const int z = o % g.Z, y = (o / g.Z) % g.Y, x = o / (g.Z * g.Y);
         const uint32_t ci = d.cellinfo[eoff + ((size_t)z * g.Y + y) * g.Xp + x];
@@ -302,9 +309,11 @@ __global__ void k_reset_env(Geo g, Dev d) {
     for (int k = 0; k < 6; k++) d.cum[6 * (size_t)env + k] = 0;
     d.wlvia[2 * env] = 0; d.wlvia[2 * env + 1] = 0;
     d.msum[4 * env] = 0; d.msum[4 * env + 1] = 0; d.msum[4 * env + 2] = 0;
+    d.minc[4 * env] = 0; d.minc[4 * env + 1] = 0; d.minc[4 * env + 2] = 0;
     d.delta[3 * env] = 0; d.delta[3 * env + 1] = 0; d.delta[3 * env + 2] = 0;
     d.reward[env] = 0.0;
     d.phase[env] = 0; d.path_n[env] = 0; d.conn_n[env] = 0;
+    d.fr_epoch[env] = 0;                                    // (k_reset_cells made every cell word stale)
     refresh_remaining(g, d, env);
     d.done[env] = d.n_remaining[env] == 0;
 }

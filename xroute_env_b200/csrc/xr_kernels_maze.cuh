@@ -33,10 +33,6 @@
 // Only the full-grid path reads these two arrays: environments whose net goes to a window kernel (mode 1) skip the
 // pass -- the window kernel derives its window's flags from cellinfo / apnet itself -- and get it lazily
 // (handover = 1, followed by k_handover_seed) in the rare step in which their search escapes the window.
-__device__ __forceinline__ uint32_t cost_flags(uint32_t cellinfo, uint32_t apnet, uint32_t net) {
-    return ((cellinfo & CI_USAGE_MASK) ? CF_RS : 0u) | ((apnet != 0u && apnet != net) ? CF_FS : 0u) |
-           ((cellinfo & CI_BLOCK) ? CF_BLK : 0u);
-}
 __global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp, int handover) {
     const int env = blockIdx.y;
     const int net = d.act[2 * env + 1];
@@ -105,6 +101,10 @@ __global__ void k_seed(Geo g, Dev d, int grp) {
         d.conn_off[(size_t)env * (g.conn_cap + 1)] = 0;
     }
     if (net == 0) return;
+    if (d.mode[env] == 2) {                               // frontier engine: it keeps its own field and source set
+        if (threadIdx.x == 0) { d.changed[env] = 0; d.reinit[env] = 0; d.first[env] = 1; d.phase[env] = 0; }
+        return;
+    }
     // full-grid bookkeeping: the first pump of a net (or of a hand-over from a window kernel) sweeps everything
     {
         const int S = g.Xp / 32;
@@ -410,21 +410,6 @@ __global__ void __launch_bounds__(32 * 16) k_sweep_y(Geo g, Dev d) {
 }
 
 // -------------------------------------------------------------------- control
-__device__ __forceinline__ void dir_delta(int dir, int &ddx, int &ddy, int &ddz) {
-    ddx = (dir == 0) - (dir == 1); ddy = (dir == 2) - (dir == 3); ddz = (dir == 4) - (dir == 5);
-}
-// weight of the move p -> c = p + delta(dir), f = flags of c (the cell entered)
-__device__ __forceinline__ uint32_t move_w(const Geo &g, int px, int py, int pz, int dir, uint32_t f) {
-    switch (dir) {
-    case 0: return wgt_x(g, pz, (uint32_t)(g.xc[px + 1] - g.xc[px]), f);
-    case 1: return wgt_x(g, pz, (uint32_t)(g.xc[px] - g.xc[px - 1]), f);
-    case 2: return wgt_y(g, pz, (uint32_t)(g.yc[py + 1] - g.yc[py]), f);
-    case 3: return wgt_y(g, pz, (uint32_t)(g.yc[py] - g.yc[py - 1]), f);
-    case 4: return wgt_v(g, pz, pz + 1, f);
-    default: return wgt_v(g, pz - 1, pz - 1, f);
-    }
-}
-
 // Commit one path cell: occupancy, obstacle channel source, tree mark, new source.
 // zero_dist = false: the caller is still walking the distance field (full-grid backtrace) and turns the path cells into
 // sources only after the walk -- a cell that became 0 under the walk could pass the predecessor test of a later cell
@@ -433,9 +418,21 @@ template <bool zero_dist = true>
 __device__ __forceinline__ void commit_cell(const Geo &g, const Dev &d, int env, int net, int x, int y, int z) {
     const size_t c = (size_t)env * g.cells_p + ((size_t)z * g.Y + y) * g.Xp + x;
     uint32_t ci = d.cellinfo[c];
+    {   // congestion counts maintained by the commits (XrConfig.metrics_mode 0; k_metrics recomputes them by a scan)
+        const uint32_t us = (ci & CI_USAGE_MASK) >> CI_USAGE_SHIFT;
+        unsigned long long *mc = reinterpret_cast<unsigned long long *>(d.minc + 4 * (size_t)env);
+        if (us == 0u) {
+            if (ci & CI_BLOCK) atomicAdd(mc + 0, 1ull);
+            if ((ci & CI_ISAP) && d.apnet[c] != (uint16_t)net) atomicAdd(mc + 1, 1ull);
+        } else if (us == 1u) {
+            if (!((ci & CI_ISAP) && d.apnet[c] != (ci & CI_OWNER_MASK))) atomicAdd(mc + 1, 1ull);
+            atomicAdd(mc + 2, 1ull);
+        } else if (us < 255u) atomicAdd(mc + 2, 1ull);
+    }
     if (((ci & CI_USAGE_MASK) >> CI_USAGE_SHIFT) < 255u) ci += 1u << CI_USAGE_SHIFT;
     if ((ci & CI_OWNER_MASK) == 0u) ci |= (uint32_t)net;
     d.cellinfo[c] = ci;
+    atomicOr(d.dist64 + c, FRW_RS);                         // frontier cell word: a wire covers the cell
     const size_t oo = ((size_t)x * g.Y + y) * g.Z + z;
     d.obst_obs[(size_t)env * g.cells_o + oo] = 1;
     d.obs[(size_t)env * g.obs_stride + oo] = 1.f;        // channel 0 of the observation, updated in place

@@ -26,7 +26,8 @@ class VecGame:
     def __init__(self, geom: Geometry, instances: list[Instance], *, device: int = 0,
                  max_nets: int | None = None, max_aps: int | None = None,
                  obs_max_nets: int = -1, path_capacity: int = 0, pumps_per_sync: int = 0,
-                 window_margin: int = 0, min_cluster: int = 0, obs_mode: int = 0):
+                 window_margin: int = 0, min_cluster: int = 0, obs_mode: int = 0, engine: int = 0,
+                 metrics_mode: int = 0):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.geom = geom
@@ -55,6 +56,7 @@ class VecGame:
         cfg.pumps_per_sync = pumps_per_sync
         cfg.window_margin, cfg.min_cluster = window_margin, min_cluster
         cfg.obs_mode = obs_mode
+        cfg.engine, cfg.metrics_mode = engine, metrics_mode
         rc = self._L.xr_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()
@@ -273,7 +275,9 @@ class VecGame:
     def route_counters(self) -> dict:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self._L.xr_route_counters(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
-        return {"window_nets": a.value, "global_nets": b.value, "window_fallbacks": c.value}
+        f, r = C.c_int64(), C.c_int64()
+        _lib.check(self._L.xr_frontier_counters(self._h, C.byref(f), C.byref(r)), self._h)
+        return {"window_nets": a.value, "global_nets": b.value, "window_fallbacks": c.value, "frontier_nets": f.value}
 
     def debug_counters(self) -> dict:
         out = (C.c_uint64 * 16)()
