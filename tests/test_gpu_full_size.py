@@ -59,7 +59,10 @@ def _check_full(preset, n_envs, n_nets, sample, seed, gen_kw=None, obs_cap=-1):
 
 def test_config2_syn256_64_envs_full_episode():
     rc = _check_full("SYN-256", 64, 32, sample=(0, 21, 42, 63), seed=20260000)
-    assert rc["frontier_nets"] == 64 * 32 and rc["global_nets"] == 0 and rc["window_nets"] == 0
+    # hybrid policy of the default engine: the frontier search for most nets, the sweep kernels for the few-pin nets
+    # with a wide bounding box (a 64-environment step does not fill the GPU with one CTA per net)
+    assert rc["frontier_nets"] + rc["window_nets"] == 64 * 32 and rc["global_nets"] == 0
+    assert rc["frontier_nets"] > 1500 and rc["window_nets"] > 50, rc
 
 
 def test_config3_t1_7x7_shard_512_envs_full_episode():

@@ -56,8 +56,8 @@ struct XrEnv {
     // window-resident route kernel
     int win_margin = 14, min_cluster = 0, smem_cap = 0, n_sm = 148;
     std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
-    int32_t *p_lists = nullptr;         // pinned [2 + XR_NB*XR_NG][N]: mode, group, env lists of the XR_NG x XR_NB cluster buckets
-    int32_t *d_lists = nullptr;         // device [XR_NB*XR_NG][N]
+    int32_t *p_lists = nullptr;         // pinned [3 + XR_NB*XR_NG][N]: mode, group, frontier list, env lists of the XR_NG x XR_NB cluster buckets
+    int32_t *d_lists = nullptr;         // device [1 + XR_NB*XR_NG][N]
     cudaStream_t gs[XR_NG] = {nullptr, nullptr, nullptr};   // one stream per post-route group
     cudaEvent_t ev_fork = nullptr, ev_join[XR_NG] = {nullptr, nullptr, nullptr};
     int grp_pins[XR_NG] = {0, 4, 8};    // group g = nets with at least grp_pins[g] pins (light / medium / heavy)
@@ -68,7 +68,9 @@ struct XrEnv {
     // frontier engine (default): one CTA per net, goal-directed search on the epoch-tagged global field
     int engine = 0;                     // 0 = frontier, 1 = window kernels + full-grid sweeps (round-1 engines)
     FrParams fr_big = {}, fr_small = {};// list capacities for "one CTA per SM" and "several CTAs per SM" launches
-    int fr_threads_big = FR_T, fr_threads_small = 256;
+    int fr_threads_big = FR_T, fr_threads_small = 512;
+    int hybrid_area = 4000, hybrid_pins = 3;   // hybrid: nets of at most hybrid_pins pins whose access-point box covers at least hybrid_area cells take the sweep kernels (0 = never)
+    std::vector<int32_t> h_area;        // [N][max_nets+1] cells of the net's access-point bounding box (x by y)
     int metrics_mode = 0;               // 0 = congestion counts maintained by the commits, 1 = full scan (k_metrics) every step
     // counters
     long long n_launch = 0, n_sync = 0;
@@ -260,7 +262,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     DA(d.phase, N); DA(d.changed, N); DA(d.reinit, N); DA(d.first, N);
     {   // everything a step uploads lives in one block (one H2D copy): act [N][2] | mode [N] | grp [N] | env lists
         int32_t *up;
-        DA(up, N * (4 + XR_NB * XR_NG));
+        DA(up, N * (5 + XR_NB * XR_NG));
         d.act = up; d.mode = up + 2 * N; d.grp = up + 3 * N; env->d_lists = up + 4 * N;
     }
     {   // ... and everything a step reads back in another (one D2H copy): cum i64 [N][6] | delta i32 [N][3] | flags i32 [4] | done u8 [N]
@@ -284,8 +286,10 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         const int cp = g.cells_p;
         env->fr_big.cap_s = 6144; env->fr_big.cap_e = 4096;
         env->fr_small.cap_s = 2048; env->fr_small.cap_e = 1024;
-        env->fr_big.delta = env->fr_small.delta = 1200u; env->fr_big.ray = env->fr_small.ray = FR_RAY;
+        env->fr_big.delta = env->fr_small.delta = 400u; env->fr_big.ray = env->fr_small.ray = FR_RAY;
         if (const char *e = getenv("XR_FR_DELTA")) env->fr_big.delta = env->fr_small.delta = (uint32_t)std::max(0, atoi(e));
+        env->fr_big.dmax = env->fr_small.dmax = 4;
+        if (const char *e = getenv("XR_FR_DMAX")) env->fr_big.dmax = env->fr_small.dmax = std::max(1, atoi(e));
         if (const char *e = getenv("XR_FR_RAY")) env->fr_big.ray = env->fr_small.ray = std::min(FR_RAY, std::max(1, atoi(e)));
         if (const char *e = getenv("XR_FR_THREADS")) env->fr_threads_big = env->fr_threads_small = std::min(FR_T, std::max(64, atoi(e) / 32 * 32));
         if (const char *e = getenv("XR_FR_CAP")) { env->fr_big.cap_s = env->fr_small.cap_s = std::max(64, atoi(e)); env->fr_big.cap_e = env->fr_small.cap_e = std::max(64, atoi(e) / 2); }
@@ -311,7 +315,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         d.obs = reinterpret_cast<float *>(q);
     }
 #undef DA
-    if (cudaMallocHost(&env->p_act, sizeof(int32_t) * (4 + XR_NB * XR_NG) * N) != cudaSuccess ||
+    if (cudaMallocHost(&env->p_act, sizeof(int32_t) * (5 + XR_NB * XR_NG) * N) != cudaSuccess ||
         cudaMallocHost(&env->p_flags, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaMallocHost(&env->p_res, (sizeof(int32_t) * 3 + sizeof(int64_t) * XR_M_COUNT + 1) * N + 64) != cudaSuccess ||
         cudaMallocHost(&env->p_ids, sizeof(int32_t) * N) != cudaSuccess ||
@@ -329,6 +333,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->h_clean.assign(N, 0);
     env->obs_mode = cfg->obs_mode == 1 ? 1 : 0;
     env->h_netwin.assign(N * (g.max_nets + 1) * 2, 0);
+    env->h_area.assign(N * (g.max_nets + 1), 0);
     env->win_margin = cfg->window_margin == 0 ? 14 : cfg->window_margin;
     // 0 = auto: per step, as many CTAs per environment as keeps about two clusters per SM's worth
     env->min_cluster = cfg->min_cluster >= 16 ? 16 : cfg->min_cluster >= 8 ? 8 : cfg->min_cluster >= 4 ? 4 : cfg->min_cluster >= 2 ? 2
@@ -357,6 +362,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     env->engine = cfg->engine == 1 ? 1 : 0;
     if (const char *e = getenv("XR_ENGINE")) env->engine = atoi(e) == 1 ? 1 : 0;
     env->metrics_mode = cfg->metrics_mode == 1 ? 1 : 0;
+    if (const char *e = getenv("XR_HYBRID_AREA")) env->hybrid_area = std::max(0, atoi(e));
+    if (const char *e = getenv("XR_HYBRID_PINS")) env->hybrid_pins = std::max(2, atoi(e));
     if (const char *e = getenv("XR_METRICS_MODE")) env->metrics_mode = atoi(e) == 1 ? 1 : 0;
     ce = xr_frontier_init(env->smem_cap);
     if (ce != cudaSuccess) { std::string m = std::string("frontier kernel attribute: ") + cudaGetErrorString(ce); xr_free(env); return fail(nullptr, XR_E_CUDA, m); }
@@ -462,6 +469,7 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
         }
         npins[net] = (uint16_t)std::min(np, 65535);
         env->h_naps[(size_t)env_id * (g.max_nets + 1) + net] = t - s;
+        env->h_area[(size_t)env_id * (g.max_nets + 1) + net] = (xmax - xmin + 1) * (ymax - ymin + 1);
         const int cx2 = xmin + xmax, cy2 = ymin + ymax;
         long best = -1; int bp = 0;
         for (int k = s; k < t; k++) {
@@ -724,6 +732,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         while (min_cluster < 8 && n_route * min_cluster * 2 <= 2 * env->n_sm) min_cluster <<= 1;
     }
     bool any_global = false, any_win = false;
+    int fr_grp = 0, n_routing = 0;
+    for (int i = 0; i < g.N; i++) n_routing += actions[i] >= 1 && env->h_npins[(size_t)i * (g.max_nets + 1) + actions[i]] >= 2;
+    const bool hybrid = env->hybrid_area > 0 && n_routing <= env->n_sm;
     std::vector<long long> fr_order;                      // frontier engine: (pin-count key, env), sorted before the upload
     int n_grp[XR_NG] = {}, n_glob[XR_NG] = {};            // environments per group / of them on the full-grid path
     int32_t *modes = env->p_lists, *grps = env->p_lists + g.N;   // then XR_NB*XR_NG lists of N: [group][bucket]
@@ -738,12 +749,19 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             int bucket = -1;
             const int mc = (np >= env->grp_pins[XR_NG - 1] && env->heavy_cluster > 0) ? env->heavy_cluster : min_cluster;
             if (env->engine == 0 && env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= FR_MAXAP && np <= FR_MAXPIN) {
-                // frontier engine: one CTA per net, no window; every such environment is finalised by one epilogue
-                fr_order.push_back(((long long)(65535 - std::min(np, 65535)) << 32) | (unsigned)i);   // many-pin nets first
-                env->n_frontier_nets++;
-                env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
-                modes[i] = 2; grps[i] = 0; n_grp[0]++;
-                continue;
+                // frontier engine: one CTA per net, no window.  Hybrid: when the batch is too small to fill the GPU with
+                // one CTA per net, a step is as long as its largest search, and the largest searches are the few-pin
+                // nets with a wide bounding box (the search floods the box on ~3 layers: the sweep kernels do that
+                // faster on a cluster of CTAs).  Same results either way.
+                const bool wide = hybrid && np <= env->hybrid_pins && WX > 0 && WX < 1024 && WY < 1024 &&
+                                  env->h_area[(size_t)i * (g.max_nets + 1) + a] >= env->hybrid_area;
+                if (!wide) {
+                    fr_order.push_back(((long long)(65535 - std::min(np, 65535)) << 32) | (unsigned)i);   // many-pin nets first
+                    env->n_frontier_nets++;
+                    env->p_act[2 * i] = a; env->p_act[2 * i + 1] = route;
+                    modes[i] = 2; grps[i] = -1;            // (group assigned below)
+                    continue;
+                }
             }
             if (WX > 0 && env->dual_pins > 0 && np >= env->dual_pins && WX < 1024 && WY < 1024 &&
                 env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= WIN_TGT_CAP) {
@@ -766,7 +784,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (bucket < 0) grp = XR_NG - 1;
             if (bucket >= 0) {
                 mode = 1; any_win = true;
-                env->p_lists[(size_t)(2 + grp * XR_NB + bucket) * g.N + nb[grp][bucket]++] = i;
+                env->p_lists[(size_t)(3 + grp * XR_NB + bucket) * g.N + nb[grp][bucket]++] = i;
                 env->n_win_nets++;
             } else { any_global = true; env->n_global_nets++; n_glob[grp]++; }
         }
@@ -775,11 +793,16 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         modes[i] = mode; grps[i] = grp;
     }
     const int n_fr = (int)fr_order.size();
-    if (n_fr) {                                           // the frontier list rides in the (group 0, bucket 0) slot
+    {   // frontier nets finish in one group of their own: the heaviest group's stream when sweep kernels run beside them
+        const int fg = (any_win || any_global) ? XR_NG - 1 : 0;
+        for (int i = 0; i < g.N; i++) if (grps[i] < 0) { grps[i] = fg; n_grp[fg]++; }
+        fr_grp = fg;
+    }
+    if (n_fr) {                                           // the frontier list rides in front of the bucket lists
         std::sort(fr_order.begin(), fr_order.end());
         for (int k = 0; k < n_fr; k++) env->p_lists[(size_t)2 * g.N + k] = (int32_t)(fr_order[k] & 0xFFFFFFFFll);
     }
-    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * (size_t)(any_route ? (any_win || any_global ? 4 + XR_NB * XR_NG : 5) : 4) * g.N,
+    CK(cudaMemcpyAsync(env->d.act, env->p_act, sizeof(int32_t) * (size_t)(any_route ? (any_win || any_global ? 5 + XR_NB * XR_NG : 5) : 4) * g.N,
                        cudaMemcpyHostToDevice, st));       // act | mode | grp | env lists in one copy
     // ---- the two post-route groups run on their own streams: the light group's metric and
     // observation kernels (HBM bound) overlap the heavy group's on-chip routing
@@ -812,7 +835,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             if (n_glob[grp]) { Launch L(env, XR_K_ROUTE_BEGIN, sg); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, sg>>>(env->g, env->d, grp, 0); }
             { Launch L(env, XR_K_MISC, sg); k_seed<<<g.N, 64, 0, sg>>>(env->g, env->d, grp); }
         }
-        if (grp == 0 && n_fr) {
+        if (grp == fr_grp && n_fr) {
             const bool big = n_fr <= env->n_sm;
             Launch L(env, XR_K_ROUTE_FRONTIER, sg);
             cudaError_t e = xr_frontier_launch(env->g, env->d, env->d_lists, n_fr, big ? env->fr_big : env->fr_small,
@@ -821,7 +844,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         }
         for (int b = XR_NB - 1; b >= 0; b--) {              // widest clusters first: they need a whole GPC
             if (!nb[grp][b]) continue;
-            int rc = launch_route_win(env, sg, CS[b], b >= NB_BAND, nb[grp][b], env->d_lists + (size_t)(grp * XR_NB + b) * g.N);
+            int rc = launch_route_win(env, sg, CS[b], b >= NB_BAND, nb[grp][b], env->d_lists + (size_t)(1 + grp * XR_NB + b) * g.N);
             if (rc != XR_OK) return rc;
         }
         if (has && env->metrics_mode == 1) { Launch L(env, XR_K_METRICS, sg); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, sg>>>(env->g, env->d, grp); }

@@ -43,6 +43,7 @@ struct FrSm {
     int pn, cn, walk_fail;
     unsigned long long best;
     int rx0, rx1, ry0, ry1;  // tiles holding the net's access points
+    int dmul;              // current bucket width in units of delta
 };
 
 __device__ __forceinline__ int fr_agg_inc(int *ctr) {
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
         auto dval = [&](unsigned long long v) -> uint32_t { return (uint32_t)(v >> 34) == hi ? ((uint32_t)(v >> 4) & 0x3FFFFFFFu) : XR_INF; };
         if (tid == 0) {
             S->cnt[0] = 0; S->cnt[1] = 0; S->fmin[0] = 0xFFFFFFFFu; S->fmin[1] = 0xFFFFFFFFu;
-            S->nexp[0] = 0; S->nexp[1] = 0; S->nray[0] = 0; S->nray[1] = 0; S->B = XR_INF; S->nbox = 0; S->best = ~0ull;
+            S->nexp[0] = 0; S->nexp[1] = 0; S->nray[0] = 0; S->nray[1] = 0; S->B = XR_INF; S->nbox = 0; S->best = ~0ull; S->dmul = 1;
         }
         // ---- the tree so far becomes the source set of this epoch (distance 0; the flag bits of a word stay)
         if (first) {
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
             const uint32_t fm = S->fmin[cur], Bv = S->B;
             if (n == 0 || fm > Bv) break;
             n_rounds++;
-            const uint32_t thr = fm + P.delta;
+            const uint32_t thr = fm + P.delta * (uint32_t)S->dmul;
             const int nxt = cur ^ 1;
             uint32_t fl = 0xFFFFFFFFu;
             // classify: expand now (one single-step task + a ray task per ray bit) / keep for later / drop (f > B)
@@ -350,7 +351,12 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
 #ifdef FR_TIMING
             n_expanded += nE; max_open = max(max_open, (long long)n);
 #endif
-            if (tid == 0) { S->cnt[cur] = 0; S->fmin[cur] = 0xFFFFFFFFu; S->nexp[par ^ 1] = 0; S->nray[par ^ 1] = 0; }
+            if (tid == 0) {
+                S->cnt[cur] = 0; S->fmin[cur] = 0xFFFFFFFFu; S->nexp[par ^ 1] = 0; S->nray[par ^ 1] = 0;
+                // bucket width: a round costs the same (one L2 round trip + two barriers) whether it expands ten
+                // entries or a thousand -- widen the bucket while rounds are nearly empty, narrow it when they are wide
+                if (nE < T / 16) S->dmul = min(S->dmul * 2, P.dmax); else if (nE > 2 * T) S->dmul = max(S->dmul / 2, 1);
+            }
             // a lowered cell that is an access point of this net: a target if its pin is unconnected
             auto target_check = [&](size_t idx, uint32_t nd) {
                 for (int i = 0; i < n_ap; i++)
@@ -374,7 +380,10 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
             // distances, the ray ends at the first cell it does not lower.  Only the last cell of a full-length ray
             // shoots on (same direction); the others were relaxed onwards by this very ray, and backwards lies the
             // smaller distance they came from.
-            for (int w0 = warp * 32; w0 < FR_RAY * nR; w0 += T) {
+            // Ray lanes first, single-step lanes behind them (from a warp boundary on), dealt to the warps round robin.
+            const int R32 = (FR_RAY * nR + 31) & ~31;
+            for (int w0 = warp * 32; w0 < R32 + 4 * nE; w0 += T) {
+              if (w0 < R32) {
                 const int w = w0 + lane;
                 const bool act = w < FR_RAY * nR;
                 const int t = act ? w / FR_RAY : 0, k = w & (FR_RAY - 1);
@@ -422,10 +431,9 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 if (low) fv = nd + hval(xv, yv);
                 const uint32_t on = (k == m - 1 && m == P.ray) ? (sgn > 0 ? FR_RAY_POS : FR_RAY_NEG) : 0u;
                 push(low && fv <= B2, (uint32_t)(xv | (yv << 10) | (z << 20)) | on, fv);
-            }
-            // ---- single-step tasks, one lane per cell: the two wrong-way neighbours and the two vias of every expanded cell
-            for (int w0 = warp * 32; w0 < 4 * nE; w0 += T) {
-                const int w = w0 + lane;
+              } else {
+                // ---- single-step tasks, one lane per cell: the two wrong-way neighbours and the two vias of every expanded cell
+                const int w = w0 - R32 + lane;
                 const bool act = w < 4 * nE;
                 const int t = act ? w >> 2 : 0, j = w & 3;
                 uint32_t pc, d0;
@@ -461,6 +469,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 uint32_t fv = 0;
                 if (low) fv = nd + hval(xv, yv);
                 push(low && fv <= B2, (uint32_t)(xv | (yv << 10) | (zv << 20)) | FR_RAYS_BOTH, fv);
+              }
             }
             fl = __reduce_min_sync(0xFFFFFFFFu, fl);
             if (lane == 0 && fl != 0xFFFFFFFFu) atomicMin(&S->fmin[nxt], fl);

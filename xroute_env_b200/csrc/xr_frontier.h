@@ -19,6 +19,7 @@ struct FrParams {
     int cap_ge;            // expansion-list entries that may spill
     uint32_t delta;        // entries with f <= (smallest open f) + delta are expanded in the same round (cost units)
     int ray;               // 1..FR_RAY
+    int dmax;              // the bucket may widen to dmax * delta while rounds are nearly empty (1 = fixed width)
 };
 
 size_t xr_frontier_smem(const Geo &g, const FrParams &P);
