@@ -287,6 +287,16 @@ def test_path_capacity_overflow_fails_the_step():
     with pytest.raises(RuntimeError, match="path_capacity"):
         for net in insts[0].net_ids:
             vg.step(np.array([net], np.int32))
+    # the failed step left the batch half-stepped: the handle refuses to step until the environments are reset
+    from xroute_env_b200._lib import XrError, XR_E_STATE
+    with pytest.raises(XrError) as ei:
+        vg.step(np.array([insts[0].net_ids[-1]], np.int32))
+    assert ei.value.code == XR_E_STATE
+    vg.reset()
+    assert vg.legal_set(0) == set(insts[0].net_ids)
+    with pytest.raises(RuntimeError, match="path_capacity"):
+        for net in insts[0].net_ids:
+            vg.step(np.array([net], np.int32))
     vg.close()
 
 

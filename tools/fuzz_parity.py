@@ -40,6 +40,18 @@ while time.time() - t0 < budget and not bad:
     kw = dict(window_margin=int(rng.choice([-1, 0, 0, 0, 1, 4, 30])), min_cluster=int(rng.choice([0, 0, 1, 2, 4, 8, 16])),
               obs_mode=int(rng.choice([0, 0, 1])))
     dual = rng.random() < 0.5
+    # engine 0 (default): the frontier search with random ray length / bucket width / block size / list capacity and the
+    # hybrid threshold anywhere from "every net" to "no net" on the sweep kernels; engine 1: the sweep engines alone
+    kw["engine"] = int(rng.random() < 0.3)
+    kw["metrics_mode"] = int(rng.random() < 0.3)
+    knobs = {"XR_FR_RAY": str(int(rng.integers(1, 9))), "XR_FR_DELTA": str(int(rng.choice([0, 100, 400, 1200, 100000]))),
+             "XR_FR_DMAX": str(int(rng.choice([1, 4, 16]))), "XR_FR_THREADS": str(int(rng.choice([64, 256, 1024]))),
+             "XR_HYBRID_AREA": str(int(rng.choice([0, 30, 400, 4000]))), "XR_HYBRID_PINS": str(int(rng.choice([2, 3, 30])))}
+    if rng.random() < 0.3:
+        knobs["XR_FR_CAP"] = "64"
+    else:
+        os.environ.pop("XR_FR_CAP", None)
+    os.environ.update(knobs)
     for k, v in (("XR_DUAL_PINS", "2" if dual else "8"), ("XR_DUAL_MINC", str(int(rng.choice([2, 4, 8]))) if dual else "8")):
         os.environ[k] = v
     vg = VecGame(geom, insts, device=0, **kw)
@@ -48,7 +60,16 @@ while time.time() - t0 < budget and not bad:
     orders = [list(rng.permutation(i.net_ids)) for i in insts]
     for t in range(max(len(o) for o in orders)):
         acts = np.array([int(o[t]) if t < len(o) else 0 for o in orders], np.int32)
-        vg.step(acts)
+        try:
+            vg.step(acts)
+        except Exception as ex:                 # keep the configuration of a failing step for tools/repro_fuzz.py
+            import pickle
+            os.makedirs("gpurun_out", exist_ok=True)
+            with open("gpurun_out/fuzz_fail.pkl", "wb") as fh:
+                pickle.dump(dict(geom=geom, insts=insts, kw=kw, knobs=knobs, dual=dual, orders=orders, t=t,
+                                 env={k: os.environ.get(k) for k in ("XR_DUAL_PINS", "XR_DUAL_MINC")}), fh)
+            bad.append(dict(shape=(X, Y, Z), kw=kw, knobs=knobs, t=t, error=str(ex)))
+            break
         delta, done, cum = vg.results_host()
         for e, o in enumerate(orcs):
             if acts[e] == 0:
@@ -61,13 +82,15 @@ while time.time() - t0 < budget and not bad:
                 ok = np.array_equal(vg.obs_host(e).numpy(), o.obs())
             if not ok:
                 pins = len(set(insts[e].ap_pin[insts[e].ap_net == acts[e]].tolist()))
-                bad.append(dict(shape=(X, Y, Z), uniform=uniform, n_env=n_env, n_nets=n_nets, iseed=iseed, pob=pob, kw=kw, dual=dual,
+                bad.append(dict(shape=(X, Y, Z), uniform=uniform, n_env=n_env, n_nets=n_nets, iseed=iseed, pob=pob, kw=kw, dual=dual, knobs=knobs,
                                 minc=os.environ["XR_DUAL_MINC"], t=t, e=e, net=int(acts[e]), pins=pins,
                                 cost_o=ocost.tolist()[:6], cost_g=gcost.tolist()[:6], path_eq=bool(np.array_equal(oc, gc)),
                                 cum_g=[int(v) for v in cum[e]], cum_o=[m["violation"], m["wirelength"], m["via"]],
                                 rc=vg.route_counters()))
             n_steps += 1
     for e, o in enumerate(orcs):
+        if bad:
+            break
         if not (np.array_equal(vg.state(e)[0], o.state()[0]) and np.array_equal(vg.state(e)[1], o.state()[1])):
             bad.append(dict(shape=(X, Y, Z), kw=kw, dual=dual, what="state", e=e))
     vg.close()

@@ -293,7 +293,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         if (const char *e = getenv("XR_FR_RAY")) env->fr_big.ray = env->fr_small.ray = std::min(FR_RAY, std::max(1, atoi(e)));
         if (const char *e = getenv("XR_FR_THREADS")) env->fr_threads_big = env->fr_threads_small = std::min(FR_T, std::max(64, atoi(e) / 32 * 32));
         if (const char *e = getenv("XR_FR_CAP")) { env->fr_big.cap_s = env->fr_small.cap_s = std::max(64, atoi(e)); env->fr_big.cap_e = env->fr_small.cap_e = std::max(64, atoi(e) / 2); }
-        const int cap_g = std::max(cp / 4, 32768), cap_ge = std::max(cp / 8, 16384);
+        const int cap_g = std::max(cp, 32768), cap_ge = std::max(cp / 2, 16384);
         env->fr_big.cap_g = env->fr_small.cap_g = cap_g; env->fr_big.cap_ge = env->fr_small.cap_ge = cap_ge;
         DA(d.dist64, N * g.cells_p);
         ce = cudaMemset(d.dist64, 0xFF, sizeof(unsigned long long) * N * g.cells_p);
@@ -692,6 +692,18 @@ static int launch_route_win(XrEnv *env, cudaStream_t st, int C, bool dual, int n
     return XR_OK;
 }
 
+// A route kernel reported an error (device flag): 4 = path record overflow, 5 = open list overflow of the frontier
+// engine, 1 = unreachable target, 2 / 3 = no predecessor during the walk.  The batch is left half-stepped (some
+// environments finalised, the failing one partially committed): the handle refuses further steps until every
+// environment has been reset (XR_E_STATE), which restores a consistent state.
+static int step_failed(XrEnv *env, int code) {
+    std::fill(env->h_reset.begin(), env->h_reset.end(), 0);
+    env->res_on_host = false;
+    if (code == 4) return fail(env, XR_E_CAPACITY, "a net's paths exceed path_capacity (XrConfig.path_capacity); reset the environments before stepping again");
+    if (code == 5) return fail(env, XR_E_CAPACITY, "frontier search: open list overflow (more live entries than cells); reset the environments before stepping again");
+    return fail(env, XR_E_UNROUTABLE, "maze search failed (no path / inconsistent backtrace); reset the environments before stepping again");
+}
+
 extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     if (!env || !actions) return XR_E_INVALID;
     const Geo &g = env->g;
@@ -870,10 +882,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         CK(cudaStreamSynchronize(st)); env->n_sync++;
         memcpy(env->p_flags, env->p_res + sizeof(int64_t) * XR_M_COUNT * g.N + sizeof(int32_t) * 3 * g.N, sizeof(int32_t) * 2);
         if (env->p_flags[1] != 0) {
-            const bool cap = env->p_flags[1] == 4;
+            const int code = env->p_flags[1];
             cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
-            if (cap) return fail(env, XR_E_CAPACITY, "a net's paths exceed path_capacity (XrConfig.path_capacity)");
-            return fail(env, XR_E_UNROUTABLE, "window maze search failed (inconsistent backtrace)");
+            return step_failed(env, code);
         }
         if (env->p_flags[0] > 0) need_global = true;
         else env->res_on_host = true;
@@ -898,10 +909,9 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st)); env->n_sync++;
             if (env->p_flags[1] != 0) {
-                const bool cap = env->p_flags[1] == 4;
+                const int code = env->p_flags[1];
                 cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
-                if (cap) return fail(env, XR_E_CAPACITY, "a net's paths exceed path_capacity (XrConfig.path_capacity)");
-                return fail(env, XR_E_UNROUTABLE, "maze search failed (no path / inconsistent backtrace)");
+                return step_failed(env, code);
             }
             if (env->p_flags[0] == 0) break;
             if (pumps > guard * 64) return fail(env, XR_E_UNROUTABLE, "maze search did not converge");

@@ -319,6 +319,9 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
             if (n == 0 || fm > Bv) break;
             n_rounds++;
             const uint32_t thr = fm + P.delta * (uint32_t)S->dmul;
+            // list pressure (a quarter of the capacity in use): drop the stale entries of a cell here and push a cell only
+            // when its word really went down, so that the list holds at most one live entry per cell and lowering
+            const bool tight = n > cap_l / 4;
             const int nxt = cur ^ 1;
             uint32_t fl = 0xFFFFFFFFu;
             // classify: expand now (one single-step task + a ray task per ray bit) / keep for later / drop (f > B)
@@ -329,6 +332,10 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 if (i < P.cap_s) { const uint32_t *q = l_base + 2 * (size_t)cur * P.cap_s + i; pc = q[0]; f = q[P.cap_s]; }
                 else { const uint32_t *q = spill + 2 * (size_t)cur * P.cap_g + (i - P.cap_s); pc = __ldcg(q); f = __ldcg(q + P.cap_g); }
                 if (f > Bv) continue;
+                if (tight) {
+                    const int ex = pc & 1023, ey = (pc >> 10) & 1023, ez = (pc >> 20) & 15;
+                    if (dval(__ldcg(dist + ((size_t)ez * Y + ey) * Xp + ex)) < f - hval(ex, ey)) continue;
+                }
                 if (f <= thr) {
                     const uint32_t d0 = f - hval(pc & 1023, (pc >> 10) & 1023);
                     const int idx = fr_agg_inc(&S->nexp[par]);
@@ -421,16 +428,18 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 const int m = __ffs(~bits) - 1;                       // cells of this ray that are lowered (a prefix)
                 const bool low = valid && k < m;
                 work += fresh ? 1 : 0;
+                bool won = low;
                 if (low) {
-                    atomicMin(dist + idx, frw_make(hi, nd, (uint32_t)(wv & FRW_FLAGS)));
+                    const unsigned long long key = frw_make(hi, nd, (uint32_t)(wv & FRW_FLAGS));
+                    if (tight) won = atomicMin(dist + idx, key) > key; else atomicMin(dist + idx, key);
                     if (isown) target_check(idx, nd);
                 }
                 __syncwarp();
                 const uint32_t B2 = *(volatile uint32_t *)&S->B;
                 uint32_t fv = 0;
-                if (low) fv = nd + hval(xv, yv);
+                if (won) fv = nd + hval(xv, yv);
                 const uint32_t on = (k == m - 1 && m == P.ray) ? (sgn > 0 ? FR_RAY_POS : FR_RAY_NEG) : 0u;
-                push(low && fv <= B2, (uint32_t)(xv | (yv << 10) | (z << 20)) | on, fv);
+                push(won && fv <= B2, (uint32_t)(xv | (yv << 10) | (z << 20)) | on, fv);
               } else {
                 // ---- single-step tasks, one lane per cell: the two wrong-way neighbours and the two vias of every expanded cell
                 const int w = w0 - R32 + lane;
@@ -460,15 +469,17 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 const uint32_t Bnow = *(volatile uint32_t *)&S->B;
                 const bool low = fresh && nd <= Bnow && nd < dval(wv);
                 work += fresh ? 1 : 0;
+                bool won = low;
                 if (low) {
-                    atomicMin(dist + idx, frw_make(hi, nd, (uint32_t)(wv & FRW_FLAGS)));
+                    const unsigned long long key = frw_make(hi, nd, (uint32_t)(wv & FRW_FLAGS));
+                    if (tight) won = atomicMin(dist + idx, key) > key; else atomicMin(dist + idx, key);
                     if (isown) target_check(idx, nd);
                 }
                 __syncwarp();
                 const uint32_t B2 = *(volatile uint32_t *)&S->B;
                 uint32_t fv = 0;
-                if (low) fv = nd + hval(xv, yv);
-                push(low && fv <= B2, (uint32_t)(xv | (yv << 10) | (zv << 20)) | FR_RAYS_BOTH, fv);
+                if (won) fv = nd + hval(xv, yv);
+                push(won && fv <= B2, (uint32_t)(xv | (yv << 10) | (zv << 20)) | FR_RAYS_BOTH, fv);
               }
             }
             fl = __reduce_min_sync(0xFFFFFFFFu, fl);
