@@ -137,12 +137,21 @@ int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, const int32_t 
  * rebuild their observations.  Asynchronous on `stream`.                        */
 int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *stream);
 
-/* One environment step for the whole batch.  actions: HOST int32 [N]; >=1 = net id
- * to route (1-based, as Game.step), 0 = leave this environment untouched, -1 = stop
- * (marks it done).  Routes, commits, updates metrics and rebuilds observations.
- * Returns XR_E_ILLEGAL (nothing changed) if any action is not legal.  The route
- * loop polls a device flag, the trailing metric/observation kernels are left
- * asynchronous on `stream`.                                                     */
+/* One environment step for the whole batch.  actions: HOST int32 [N]; >=1 = net id to route (1-based, as Game.step),
+ * 0 = leave this environment untouched, -1 = stop (marks it done).  Routes, commits, updates metrics and observations.
+ * Returns XR_E_ILLEGAL (nothing changed) if any action is not legal.
+ *   xr_step_async  validates on the host mirror, uploads the actions and enqueues every kernel of the step plus the
+ *                  read-back of its results on `stream`; it never blocks on the device.  The actions array may be reused
+ *                  as soon as it returns.  One step may be in flight per handle (XR_E_STATE otherwise).
+ *   xr_step_wait   blocks until that step is complete (one event wait) and reports device-side errors.  Nets whose
+ *                  search must run on the full-grid sweeps (engine 1 only, or nets too large for the on-chip tables)
+ *                  are finished here: that loop polls a device flag every `pumps_per_sync` iterations.
+ *   xr_step        = xr_step_async + xr_step_wait.
+ * Every other entry point that touches the state (reset, results, exports) completes a pending step first.
+ * A step that fails on the device (XR_E_CAPACITY, XR_E_UNROUTABLE) leaves the batch half-stepped: every environment must
+ * be reset before the handle steps again (XR_E_STATE until then).                                                     */
+int xr_step_async(XrEnv *env, const int32_t *actions, void *stream);
+int xr_step_wait(XrEnv *env);
 int xr_step(XrEnv *env, const int32_t *actions, void *stream);
 
 /* Copy the last step's results to HOST buffers (any may be NULL) and synchronise:
@@ -177,6 +186,12 @@ int xr_get_dist(XrEnv *env, int32_t env_id, uint32_t *dist);                    
 
 /* Refresh XR_BUF_STATS from the per-environment counters (asynchronous).        */
 int xr_stats_update(XrEnv *env, void *stream);
+
+/* Multi-GPU: refresh XR_BUF_STATS and all-reduce it (SUM, int64 [XR_STATS_COUNT]) in place over the ranks of
+ * `nccl_comm` (an ncclComm_t, passed as void*), asynchronously on `stream`.  The only collective of the path: the
+ * environments of a job are sharded over the GPUs and never exchange data.  NCCL is taken
+ * from the process at run time (the library the communicator was created with); no link-time dependency.      */
+int xr_stats_allreduce(XrEnv *env, void *nccl_comm, void *stream);
 
 /* Counters since creation: kernel launches issued by this library and relaxation
  * passes / cells relaxed by the maze kernels.                                   */

@@ -300,6 +300,36 @@ def test_path_capacity_overflow_fails_the_step():
     vg.close()
 
 
+def test_step_async_and_wait():
+    """xr_step_async enqueues a step without blocking; xr_step_wait (or any call that reads state) completes it; a second
+    step before that is a call-sequence error.  Results equal the synchronous path's."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    from xroute_env_b200._lib import XrError, XR_E_STATE
+    geom = ispd18_geometry(40, 36, 9)
+    insts = make_batch(geom, 4, 6, seed=7)
+    vg = VecGame(geom, insts, device=0)
+    vg.reset()
+    orcs = [OracleEnv(geom, i) for i in insts]
+    order = insts[0].net_ids
+    for k, net in enumerate(order):
+        acts = np.array([net] * 4, np.int32)
+        vg.step_async(acts)
+        acts[:] = 0                                             # the array may be reused at once
+        if k == 1:
+            with pytest.raises(XrError) as ei:
+                vg.step_async(np.array([order[-1]] * 4, np.int32))
+            assert ei.value.code == XR_E_STATE
+        if k % 2 == 0:
+            vg.step_wait()
+        delta, done, cum = vg.results_host()                    # completes the pending step when nobody waited
+        for e, o in enumerate(orcs):
+            m = o.step(net)
+            assert [int(v) for v in cum[e]] == [m["violation"], m["wirelength"], m["via"], m["blocked"], m["shorted"], m["overflow"]]
+            assert np.array_equal(vg.obs_host(e).numpy(), o.obs())
+    vg.close()
+
+
 def test_window_fallback_counter_and_exactness():
     from xroute_env_b200 import VecGame
     geom = ispd18_geometry(64, 64, 9)
@@ -536,6 +566,7 @@ def test_stop_idle_single_pin_and_state_errors():
     assert [int(v) for v in delta[1]] == [0, 0, 0] and vg.legal_set(1) == {1, 2, 3} and not int(done[1])
     assert np.array_equal(vg.obs_host(1).numpy(), obs1_before.numpy())
     assert int(done[2]) == 1 and [int(v) for v in delta[2]] == [0, 0, 0]
+    assert vg.legal.cpu()[2].sum().item() == 0 and vg.legal_set(2) == set()      # a stopped environment offers no action
     with pytest.raises(XrError):
         vg.step(np.array([0, 0, 2], np.int32))                      # environment 2 is stopped
     vg.step(np.array([3, 2, 0], np.int32))

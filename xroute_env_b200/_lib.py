@@ -53,11 +53,11 @@ class IllegalAction(XrError):
 # every symbol include/xroute_b200.h declares (tests/test_abi.py checks the two agree)
 SYMBOLS = [
     "xr_version", "xr_create", "xr_destroy", "xr_last_error", "xr_load_instance", "xr_reset",
-    "xr_step", "xr_step_results", "xr_obs_layout", "xr_obs_channels", "xr_obs_copy",
+    "xr_step", "xr_step_async", "xr_step_wait", "xr_step_results", "xr_obs_layout", "xr_obs_channels", "xr_obs_copy",
     "xr_obs_dlpack", "xr_buffer_dlpack", "xr_buffer_ptr", "xr_legal_mask", "xr_get_paths",
     "xr_get_state", "xr_get_dist", "xr_stats_update", "xr_counters", "xr_profile_enable",
     "xr_profile_get", "xr_build_obs_from_nodes", "xr_route_counters", "xr_debug_counters", "xr_debug_timeline", "xr_kernel_bench",
-    "xr_frontier_counters", "xr_debug_env_records",
+    "xr_frontier_counters", "xr_debug_env_records", "xr_stats_allreduce",
 ]
 
 _lib = None
@@ -88,6 +88,10 @@ def load():
     L.xr_reset.argtypes = [vp, i32p, C.c_int32, vp]
     L.xr_step.restype = C.c_int
     L.xr_step.argtypes = [vp, i32p, vp]
+    L.xr_step_async.restype = C.c_int
+    L.xr_step_async.argtypes = [vp, i32p, vp]
+    L.xr_step_wait.restype = C.c_int
+    L.xr_step_wait.argtypes = [vp]
     L.xr_step_results.restype = C.c_int
     L.xr_step_results.argtypes = [vp, i32p, u8p, i64p, vp]
     L.xr_obs_layout.restype = C.c_int
@@ -112,6 +116,8 @@ def load():
     L.xr_get_dist.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint32)]
     L.xr_stats_update.restype = C.c_int
     L.xr_stats_update.argtypes = [vp, vp]
+    L.xr_stats_allreduce.restype = C.c_int
+    L.xr_stats_allreduce.argtypes = [vp, vp, vp]
     L.xr_counters.restype = C.c_int
     L.xr_counters.argtypes = [vp, i64p, i64p, i64p, i64p]
     L.xr_route_counters.restype = C.c_int

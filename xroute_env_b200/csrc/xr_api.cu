@@ -15,6 +15,7 @@
 #include "xr_frontier.h"
 
 #include <algorithm>
+#include <dlfcn.h>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -85,6 +86,9 @@ struct XrEnv {
     double tl_sum[XR_NG][3] = {};   // per group: route start / route end / obs end offsets (ms)
     long long tl_n[XR_NG][3] = {};
     long long prof_n[XR_K_COUNT] = {0};
+    // a step enqueued by xr_step_async and not yet completed by xr_step_wait
+    struct { bool active = false, any_route = false, any_global = false, any_win = false; int maxn = 0; cudaStream_t st = nullptr; } pend;
+    cudaEvent_t ev_done = nullptr;
     std::atomic<int> refs{1};           // handle + outstanding DLPack tensors
 };
 
@@ -156,6 +160,7 @@ static void prof_collect(XrEnv *env) {
 
 // ----------------------------------------------------------------- create/destroy
 extern "C" int xr_version(void) { return XR_VERSION; }
+extern "C" int xr_step_wait(XrEnv *env);
 
 extern "C" const char *xr_last_error(const XrEnv *env) {
     return env ? env->err.c_str() : g_create_error.c_str();
@@ -172,6 +177,7 @@ static void xr_free(XrEnv *env) {
 
     for (int k = 0; k < XR_NG; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+    if (env->ev_done) cudaEventDestroy(env->ev_done);
     for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : env->ev_pool) cudaEventDestroy(e);
     delete env;
@@ -359,6 +365,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&env->ev_done, cudaEventDisableTiming);
     env->engine = cfg->engine == 1 ? 1 : 0;
     if (const char *e = getenv("XR_ENGINE")) env->engine = atoi(e) == 1 ? 1 : 0;
     env->metrics_mode = cfg->metrics_mode == 1 ? 1 : 0;
@@ -391,6 +398,7 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
 extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, const int32_t *block_xyz,
                                 int32_t n_ap, const int32_t *ap_net, const int32_t *ap_pin,
                                 const int32_t *ap_xyz) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env) return XR_E_INVALID;
     const Geo &g = env->g;
     if (env_id < 0 || env_id >= g.N) return fail(env, XR_E_INVALID, "env_id out of range");
@@ -399,6 +407,9 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
         return fail(env, XR_E_INVALID, "bad instance arrays");
     cudaSetDevice(env->device);
     env->res_on_host = false;
+    // the slot holds no valid instance until this call has succeeded (the host mirrors below are rebuilt in place)
+    env->h_loaded[env_id] = 0;
+    env->h_reset[env_id] = 0;
     std::vector<uint32_t> ci((size_t)g.cells_p, 0);
     std::vector<uint16_t> an((size_t)g.cells_p, 0);
     for (int z = 0; z < g.Z; z++)
@@ -565,6 +576,7 @@ static int grid_cells(const Geo &g, int per_thread) {
 
 // ---------------------------------------------------------------------- reset
 extern "C" int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *stream) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env) return XR_E_INVALID;
     const Geo &g = env->g;
     cudaStream_t st = (cudaStream_t)stream;
@@ -704,11 +716,12 @@ static int step_failed(XrEnv *env, int code) {
     return fail(env, XR_E_UNROUTABLE, "maze search failed (no path / inconsistent backtrace); reset the environments before stepping again");
 }
 
-extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
+extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
     if (!env || !actions) return XR_E_INVALID;
     const Geo &g = env->g;
     cudaStream_t st = (cudaStream_t)stream;
     cudaSetDevice(env->device);
+    if (env->pend.active) return fail(env, XR_E_STATE, "xr_step_async: the previous step has not been completed by xr_step_wait");
     // ---- validate against the host mirror of the legal sets (state untouched on error)
     bool any_route = false;
     for (int i = 0; i < g.N; i++) {
@@ -723,8 +736,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
             return fail(env, XR_E_ILLEGAL, buf);
         }
     }
-    // p_act / p_lists are reused across calls: the previous step's uploads must have completed
-    CK(cudaStreamSynchronize(st)); env->n_sync++;
+    // (p_act / p_lists are reused across calls: xr_step_wait of the previous step waited for its uploads)
     env->cur_grp = -1;
     if (env->prof) {
         cudaEvent_t e;
@@ -872,14 +884,39 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
     }
     CK(cudaGetLastError());
     env->cur_grp = -1;
+    // ---- the results ride on the same read-back as the flags, so xr_step_results needs no second round trip
+    env->res_on_host = false;
+    if (any_route && !any_global)
+        CK(cudaMemcpyAsync(env->p_res, env->d.cum, env->rb_bytes, cudaMemcpyDeviceToHost, st));   // cum | delta | flags | done
+    CK(cudaEventRecord(env->ev_done, st));
+    env->pend.active = true; env->pend.any_route = any_route; env->pend.any_global = any_global; env->pend.any_win = any_win;
+    env->pend.st = st; env->pend.maxn = 0;
+    for (int k = 0; k < XR_NG; k++) env->pend.maxn = std::max(env->pend.maxn, maxn_grp[k]);
+    // ---- host mirror (the legal sets are a pure function of the actions; a step that fails on the device invalidates
+    // the handle until the environments are reset, see step_failed)
+    for (int i = 0; i < g.N; i++) {
+        const int a = actions[i];
+        if (a >= 1) {
+            env->h_routed[(size_t)i * (g.max_nets + 1) + a] = 1;
+            env->h_nrem[i]--;
+            if (env->h_nrem[i] == 0) env->h_done[i] = 1;
+        } else if (a == -1) env->h_done[i] = 1;
+    }
+    return XR_OK;
+}
+
+extern "C" int xr_step_wait(XrEnv *env) {
+    if (!env) return XR_E_INVALID;
+    if (!env->pend.active) return XR_OK;
+    const Geo &g = env->g;
+    cudaStream_t st = env->pend.st;
+    cudaSetDevice(env->device);
+    env->pend.active = false;
+    CK(cudaEventSynchronize(env->ev_done)); env->n_sync++;
     // ---- environments whose window search escaped, or whose window does not fit on chip,
     // are routed by the full-grid sweeps and finalised in a last pass
-    bool need_global = any_global;
-    env->res_on_host = false;
-    if (any_route && !need_global) {
-        // the results ride on the same read-back as the flags, so xr_step_results needs no second round trip
-        CK(cudaMemcpyAsync(env->p_res, env->d.cum, env->rb_bytes, cudaMemcpyDeviceToHost, st));   // cum | delta | flags | done
-        CK(cudaStreamSynchronize(st)); env->n_sync++;
+    bool need_global = env->pend.any_global;
+    if (env->pend.any_route && !need_global) {
         memcpy(env->p_flags, env->p_res + sizeof(int64_t) * XR_M_COUNT * g.N + sizeof(int32_t) * 3 * g.N, sizeof(int32_t) * 2);
         if (env->p_flags[1] != 0) {
             const int code = env->p_flags[1];
@@ -893,7 +930,7 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         // lazy prologue of the environments a window kernel handed over (they skipped k_route_begin): cost flags and
         // distance field over the whole grid, then the sources / the tree committed so far.  Both kernels return at
         // once for everybody else.
-        if (any_win) {
+        if (env->pend.any_win) {
             { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1, 1); }
             { Launch L(env, XR_K_MISC, st); k_handover_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
         }
@@ -914,14 +951,12 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
                 return step_failed(env, code);
             }
             if (env->p_flags[0] == 0) break;
-            if (pumps > guard * 64) return fail(env, XR_E_UNROUTABLE, "maze search did not converge");
+            if (pumps > guard * 64) return step_failed(env, 2);
         }
         if (env->metrics_mode == 1) { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -1); }
         { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -1, env->metrics_mode == 0); }
         {
-            int maxn = 0;
-            for (int k = 0; k < XR_NG; k++) maxn = std::max(maxn, maxn_grp[k]);
-            const long long total = (2ll + 7ll * maxn) * g.cells;
+            const long long total = (2ll + 7ll * env->pend.maxn) * g.cells;
             Launch L(env, XR_K_OBS, st);
             if (env->obs_mode == 1)
                 k_obs<<<dim3((unsigned)((total + OBS_CHUNK - 1) / OBS_CHUNK), g.N), OBS_THREADS, 0, st>>>(env->g, env->d, 1);
@@ -929,19 +964,16 @@ extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
         }
         CK(cudaGetLastError());
     }
-    // ---- host mirror
-    for (int i = 0; i < g.N; i++) {
-        const int a = actions[i];
-        if (a >= 1) {
-            env->h_routed[(size_t)i * (g.max_nets + 1) + a] = 1;
-            env->h_nrem[i]--;
-            if (env->h_nrem[i] == 0) env->h_done[i] = 1;
-        } else if (a == -1) env->h_done[i] = 1;
-    }
     return XR_OK;
 }
 
+extern "C" int xr_step(XrEnv *env, const int32_t *actions, void *stream) {
+    const int rc = xr_step_async(env, actions, stream);
+    return rc != XR_OK ? rc : xr_step_wait(env);
+}
+
 extern "C" int xr_step_results(XrEnv *env, int32_t *delta, uint8_t *done, int64_t *cum, void *stream) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env) return XR_E_INVALID;
     const Geo &g = env->g;
     cudaStream_t st = (cudaStream_t)stream;
@@ -975,6 +1007,7 @@ extern "C" int xr_obs_channels(const XrEnv *env, int32_t env_id, int32_t *channe
     return XR_OK;
 }
 extern "C" int xr_obs_copy(XrEnv *env, int32_t env_id, float *host_out, int64_t n_floats, void *stream) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env || env_id < 0 || env_id >= env->g.N || !host_out) return XR_E_INVALID;
     const Geo &g = env->g;
     const long long need = (2ll + 7ll * std::min(env->h_nrem[env_id], g.obs_max_nets)) * g.cells;
@@ -1078,6 +1111,7 @@ extern "C" int xr_legal_mask(const XrEnv *env, int32_t env_id, uint8_t *mask, in
 // ------------------------------------------------------------- parity exports
 extern "C" int xr_get_paths(XrEnv *env, int32_t env_id, int32_t *cells, int32_t cells_cap, int32_t *n_cells,
                             int32_t *conn_off, uint32_t *conn_cost, int32_t conn_cap, int32_t *n_conn) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env || env_id < 0 || env_id >= env->g.N) return XR_E_INVALID;
     const Geo &g = env->g; const Dev &d = env->d;
     cudaSetDevice(env->device);
@@ -1101,6 +1135,7 @@ extern "C" int xr_get_paths(XrEnv *env, int32_t env_id, int32_t *cells, int32_t 
 }
 
 extern "C" int xr_get_state(XrEnv *env, int32_t env_id, uint8_t *usage, uint16_t *owner) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env || env_id < 0 || env_id >= env->g.N) return XR_E_INVALID;
     const Geo &g = env->g;
     cudaSetDevice(env->device);
@@ -1119,6 +1154,7 @@ extern "C" int xr_get_state(XrEnv *env, int32_t env_id, uint8_t *usage, uint16_t
 }
 
 extern "C" int xr_get_dist(XrEnv *env, int32_t env_id, uint32_t *dist) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env || env_id < 0 || env_id >= env->g.N || !dist) return XR_E_INVALID;
     const Geo &g = env->g;
     cudaSetDevice(env->device);
@@ -1134,11 +1170,38 @@ extern "C" int xr_get_dist(XrEnv *env, int32_t env_id, uint32_t *dist) {
 
 // ---------------------------------------------------------------- stats / prof
 extern "C" int xr_stats_update(XrEnv *env, void *stream) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env) return XR_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     cudaSetDevice(env->device);
     { Launch L(env, XR_K_MISC, st); k_stats<<<1, 256, 0, st>>>(env->g, env->d); }
     CK(cudaGetLastError());
+    return XR_OK;
+}
+
+/* Multi-GPU statistics: refresh XR_BUF_STATS and sum it over the ranks of `nccl_comm` in place.  NCCL is
+ * resolved at run time from the process (the library the caller created the communicator with), so the shared library
+ * itself has no link-time dependency on it.                                                                           */
+extern "C" int xr_stats_allreduce(XrEnv *env, void *nccl_comm, void *stream) {
+    if (!env || !nccl_comm) return XR_E_INVALID;
+    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef const char *(*errstr_fn)(int);
+    static allreduce_fn fn = nullptr;
+    static errstr_fn es = nullptr;
+    if (!fn) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);          // the copy already in the process (e.g. PyTorch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(env, XR_E_INVALID, std::string("xr_stats_allreduce: cannot load NCCL: ") + dlerror());
+        fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+        es = reinterpret_cast<errstr_fn>(dlsym(h, "ncclGetErrorString"));
+        if (!fn) return fail(env, XR_E_INVALID, "xr_stats_allreduce: ncclAllReduce not found");
+    }
+    int rc = xr_stats_update(env, stream);
+    if (rc != XR_OK) return rc;
+    const int nccl_int64 = 4, nccl_sum = 0;                                 // ncclDataType_t / ncclRedOp_t values of nccl.h
+    const int e = fn(env->d.stats, env->d.stats, XR_STATS_COUNT, nccl_int64, nccl_sum, nccl_comm, (cudaStream_t)stream);
+    if (e != 0) return fail(env, XR_E_CUDA, std::string("ncclAllReduce: ") + (es ? es(e) : "error"));
     return XR_OK;
 }
 
@@ -1192,6 +1255,7 @@ extern "C" int xr_frontier_counters(XrEnv *env, int64_t *frontier_nets, int64_t 
  * `reps` launches after one warm-up, measured with CUDA events on `stream`, and the
  * algorithmic bytes one launch moves.                                                  */
 extern "C" int xr_kernel_bench(XrEnv *env, int32_t which, int32_t reps, double *ms_out, double *bytes_out, void *stream) {
+    if (env && env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
     if (!env || reps < 1 || !ms_out) return XR_E_INVALID;
     const Geo &g = env->g;
     cudaStream_t st = (cudaStream_t)stream;

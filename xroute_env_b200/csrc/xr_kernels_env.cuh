@@ -248,6 +248,10 @@ __global__ void k_finalize(Geo g, Dev d, int pass, int use_minc) {
     if (raw < 1) {
         d.delta[3 * env] = 0; d.delta[3 * env + 1] = 0; d.delta[3 * env + 2] = 0;
         d.reward[env] = 0.0;
+        if (raw == -1) {                                    // stopped (net_ordering.proto:48): no action is legal any more
+            uint8_t *legal = d.legal + (size_t)env * (g.max_nets + 1);
+            for (int k = 0; k <= g.max_nets; k++) legal[k] = 0;
+        }
         return;
     }
     long long *cum = d.cum + 6 * (size_t)env;

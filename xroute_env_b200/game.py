@@ -57,7 +57,7 @@ class Game:
     """Game wrapper (reference-compatible, GPU-backed)."""
 
     def __init__(self, port_recv='5556', port_initial='6667', *, geometry: Geometry | None = None,
-                 instances=None, device: int = 0, max_nets: int = 64, max_aps: int = 4096):
+                 instances=None, device: int = 0, max_nets: int = 64, max_aps: int = 4096, pinned_ring: int = 3):
         # the two ports are accepted for signature compatibility; there is no socket
         self.port_recv = port_recv
         self.port_initial = port_initial
@@ -69,6 +69,20 @@ class Game:
         self._device = device
         self._max_nets, self._max_aps = max_nets, max_aps
         self.routed_nets = set()
+        # Observations are returned as views of a small ring of pinned host buffers (device-to-host at PCIe speed, no
+        # extra host copy): a returned tensor stays valid for the next pinned_ring - 1 reset/step calls, which covers
+        # the agents' use (state -> numpy -> network input, baseline/PPO/PPO.py:209-213).  pinned_ring = 0 returns a
+        # fresh pageable tensor per call, exactly like the reference.
+        self._ring_n, self._ring, self._ring_i = pinned_ring, [], 0
+
+    def _obs(self):
+        if self._ring_n <= 0 or not torch.cuda.is_available():
+            return self._vec.obs_host(0)
+        need = self._vec.max_channels * self.geometry.cells
+        if not self._ring or self._ring[0].numel() < need:
+            self._ring = [torch.empty(need, dtype=torch.float32, pin_memory=True) for _ in range(self._ring_n)]
+        self._ring_i = (self._ring_i + 1) % self._ring_n
+        return self._vec.obs_host(0, out=self._ring[self._ring_i])
 
     def _ensure(self, inst: Instance):
         need_nets = int(inst.ap_net.max()) if len(inst.ap_net) else 1
@@ -88,7 +102,7 @@ class Game:
         self.routed_nets.add(action)
         delta, _done, _cum = self._vec.results_host()
         violation, wirelength, via = (int(v) for v in delta[0])
-        observation = self._vec.obs_host(0)
+        observation = self._obs()
         netSet = self._vec.legal_set(0)
         done = len(netSet) == 0
         self.legal_action_set = netSet
@@ -104,7 +118,7 @@ class Game:
             self._ensure(inst)
             self._vec.reset()
             self.routed_nets = set()
-            self.observation = self._vec.obs_host(0)
+            self.observation = self._obs()
             self.action_space = self._vec.legal_set(0)
             if len(self.action_space) != 0:
                 done = False

@@ -120,6 +120,19 @@ class VecGame:
             raise ValueError(f"actions must have shape ({self.n_envs},)")
         _lib.check(self._L.xr_step(self._h, _i32p(a), self._stream()), self._h)
 
+    def step_async(self, actions):
+        """Enqueue a step without waiting for the device (``xr_step_async``); ``step_wait`` (or any call that reads
+        state) completes it.  Host work placed between the two overlaps the routing kernels."""
+        if isinstance(actions, torch.Tensor):
+            actions = actions.cpu().numpy()
+        a = np.ascontiguousarray(actions, np.int32)
+        if a.shape != (self.n_envs,):
+            raise ValueError(f"actions must have shape ({self.n_envs},)")
+        _lib.check(self._L.xr_step_async(self._h, _i32p(a), self._stream()), self._h)
+
+    def step_wait(self):
+        _lib.check(self._L.xr_step_wait(self._h), self._h)
+
     def results_host(self):
         """(delta int32 [N,3], done uint8 [N], cum int64 [N,6]) copied to pinned host memory."""
         _lib.check(self._L.xr_step_results(
@@ -207,12 +220,23 @@ class VecGame:
         _lib.check(self._L.xr_obs_dlpack(self._h, env_id, C.byref(out)), self._h)
         return torch.from_dlpack(_lib.capsule(out.value))
 
-    def obs_host(self, env_id: int) -> torch.Tensor:
-        """CPU copy of one environment's observation (what the reference's Game returns)."""
+    def obs_host(self, env_id: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """CPU copy of one environment's observation (what the reference's Game returns), float32 [1, 2+7n, Z, Y, X].
+
+        ``out``: a caller-owned CPU float32 tensor with at least ``(2+7n) * cells`` elements, ideally pinned
+        (``torch.empty(..., pin_memory=True)``): the device-to-host copy goes straight into it at PCIe speed and the
+        result is a view of it.  Without ``out`` the copy is staged through an internal pinned buffer and cloned into a
+        fresh pageable tensor the caller owns (one extra host memcpy)."""
         ch = C.c_int32()
         _lib.check(self._L.xr_obs_channels(self._h, env_id, C.byref(ch)), self._h)
         g = self.geom
         n = ch.value * g.cells
+        if out is not None:
+            if out.dtype != torch.float32 or out.device.type != "cpu" or not out.is_contiguous() or out.numel() < n:
+                raise ValueError("out must be a contiguous CPU float32 tensor with room for the observation")
+            _lib.check(self._L.xr_obs_copy(self._h, env_id, C.cast(out.data_ptr(), C.POINTER(C.c_float)), out.numel(),
+                                           self._stream()), self._h)
+            return out.view(-1)[:n].view(1, ch.value, g.Z, g.Y, g.X)
         # through a pinned staging buffer (a pageable destination makes the driver stage the copy itself,
         # several times slower), then one host memcpy into the fresh tensor the caller owns
         if self._pin_obs is None and torch.cuda.is_available() and self.max_channels * g.cells * 4 <= (2 << 30):
@@ -264,6 +288,12 @@ class VecGame:
     def stats(self) -> torch.Tensor:
         """int64 [16] per-handle sums on the GPU (all-reduce with SUM across ranks)."""
         _lib.check(self._L.xr_stats_update(self._h, self._stream()), self._h)
+        return self._buffer(_lib.XR_BUF_STATS)
+
+    def stats_allreduce(self, nccl_comm: int) -> torch.Tensor:
+        """``stats()`` summed in place over the ranks of an ``ncclComm_t`` (given as an integer address) by the library
+        itself (``xr_stats_allreduce``): the multi-GPU path of a consumer that does not use ``torch.distributed``."""
+        _lib.check(self._L.xr_stats_allreduce(self._h, C.c_void_p(nccl_comm), self._stream()), self._h)
         return self._buffer(_lib.XR_BUF_STATS)
 
     def counters(self) -> dict:

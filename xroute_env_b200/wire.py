@@ -248,7 +248,10 @@ class BatchDispatcher:
             self.cv.notify_all()
             while env not in self.done and not self.stop:
                 self.cv.wait(0.05)
-            return self.done.pop(env, None)
+            res = self.done.pop(env, None)
+        if isinstance(res, Exception):               # the batched step failed: every caller of that batch sees why
+            raise res
+        return res
 
     def _run(self):
         while not self.stop:
@@ -263,13 +266,16 @@ class BatchDispatcher:
             acts = np.zeros(self.vg.n_envs, np.int32)
             for e, a in batch.items():
                 acts[e] = a
-            with self.lock:
-                self.vg.step(acts)
-                _, _, cum = self.vg.results_host()
+            try:
+                with self.lock:
+                    self.vg.step(acts)
+                    _, _, cum = self.vg.results_host()
+                res = {e: [int(v) for v in cum[e][:3]] for e in batch}
+            except Exception as exc:                 # illegal action, capacity error ...: hand it to every waiting caller
+                res = {e: exc for e in batch}
             self.batches += 1
             with self.cv:
-                for e in batch:
-                    self.done[e] = [int(v) for v in cum[e][:3]]
+                self.done.update(res)
                 self.cv.notify_all()
 
     def close(self):
@@ -286,9 +292,10 @@ class VecGameBackend:
         self.vg, self.env, self.dispatcher = vg, env, dispatcher
         self.geom, self.inst = vg.geom, vg.insts[env]
         self.cum = [0, 0, 0]
+        self._lock = dispatcher.lock if dispatcher else threading.Lock()   # the C handle is not thread-safe
 
     def _locked(self):
-        return self.dispatcher.lock if self.dispatcher else threading.Lock()
+        return self._lock
 
     def reset(self):
         with self._locked():
@@ -305,9 +312,10 @@ class VecGameBackend:
             return
         acts = np.zeros(self.vg.n_envs, np.int32)
         acts[self.env] = net_id
-        self.vg.step(acts)
-        _, _, cum = self.vg.results_host()
-        self.cum = [int(v) for v in cum[self.env][:3]]
+        with self._locked():
+            self.vg.step(acts)
+            _, _, cum = self.vg.results_host()
+            self.cum = [int(v) for v in cum[self.env][:3]]
 
     def usage(self):
         with self._locked():
