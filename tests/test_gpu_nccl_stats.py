@@ -16,6 +16,14 @@ class _UID(C.Structure):
 
 
 def _worker(rank, world, port, out):
+    try:
+        _work(rank, world, port, out)
+    except Exception as ex:                                     # a failing rank must not leave the other one waiting
+        out.put((rank, False, repr(ex), []))
+        raise
+
+
+def _work(rank, world, port, out):
     import torch
     import torch.distributed as dist
     from xroute_env_b200 import VecGame, ispd18_geometry, make_batch
@@ -33,8 +41,8 @@ def _worker(rank, world, port, out):
     nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _UID, C.c_int]
     assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
     geom = ispd18_geometry(30, 28, 5)
-    lo, hi = shard_range(8, rank, world)
-    insts = make_batch(geom, hi - lo, 6, seed=500, first_env=lo)
+    first, count = shard_range(8, rank, world)
+    insts = make_batch(geom, count, 6, seed=500, first_env=first)
     vg = VecGame(geom, insts, device=rank)
     vg.reset()
     rng = np.random.default_rng(rank)
@@ -67,7 +75,7 @@ def test_stats_allreduce_over_a_raw_nccl_communicator():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=300) for _ in procs]
+    res = [out.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
