@@ -54,8 +54,59 @@ def full(paths):
                 print("  ", w, [r[i] for r in rows[1:]])
 
 
+def _raw(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+def _num(v):
+    try:
+        return float(v.replace(',', ''))
+    except ValueError:
+        return None
+
+
+def facts(out_json, specs):
+    """specs: name=path[:launch] ...  -> JSON of the per-launch facts bench.py quotes (launch = index of the captured launch,
+    default the last one).  Units are converted to bytes / microseconds."""
+    import json
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12, 'ns': 1e-3, 'us': 1, 'ms': 1e3, 's': 1e6, 'usecond': 1, 'msecond': 1e3, 'nsecond': 1e-3}
+    res = {}
+    for spec in specs:
+        name, rest = spec.split('=', 1)
+        path, _, idx = rest.partition(':')
+        hdr, units, rows = _raw(path)
+        r = rows[int(idx) if idx else -1]
+        def get(metric):
+            if metric not in hdr:
+                return None
+            i = hdr.index(metric)
+            v = _num(r[i])
+            return None if v is None else v * scale.get(units[i], 1)
+        rd, wr = get('dram__bytes_read.sum'), get('dram__bytes_write.sum')
+        res[name] = {
+            "source": f"profiles/{path.split('/')[-1].replace('.ncu-rep', '.txt')} (ncu --set full, launch {idx or 'last'} of the capture)",
+            "kernel": r[hdr.index('Kernel Name')].split('(')[0],
+            "dram_bytes_per_launch": None if rd is None else rd + wr,
+            "dram_bytes_read": rd, "dram_bytes_write": wr,
+            "duration_us_under_ncu": get('gpu__time_duration.sum'),
+            "issue_slots_busy_pct": get('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+            "sm_busy_pct": get('sm__throughput.avg.pct_of_peak_sustained_elapsed'),
+            "dram_throughput_pct": get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
+            "warps_active_pct": get('sm__warps_active.avg.pct_of_peak_sustained_active'),
+            "grid": get('launch__grid_size'), "block": get('launch__block_size'), "registers": get('launch__registers_per_thread'),
+            "waves_per_sm": get('launch__waves_per_multiprocessor'),
+        }
+    with open(out_json, 'w') as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "facts":
+        facts(sys.argv[2], sys.argv[3:])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
     else:
         full(sys.argv[2:])

@@ -8,15 +8,17 @@ preset = sys.argv[1] if len(sys.argv) > 1 else "SYN-256"
 n_envs = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 n_nets = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 geom = preset_geometry(preset)
-insts = make_batch(geom, n_envs, n_nets, 20260000)
+kw = dict(hot_spots=16, hot_sigma=32.0) if preset == "SYN-1024" else {}
+insts = make_batch(geom, n_envs, n_nets, 20260000, **kw)
+n_steps = int(sys.argv[4]) if len(sys.argv) > 4 else n_nets
 rng = np.random.default_rng(1)
 orders = np.stack([rng.permutation(i.net_ids) for i in insts], 1).astype(np.int32)
-vg = VecGame(geom, insts, device=0)
+vg = VecGame(geom, insts, device=0, obs_max_nets=8 if preset == 'SYN-1024' else -1)
 vg.reset()
 rec = (C.c_uint64 * (8 * n_envs))()
 worst = []
 allrec = []
-for t in range(n_nets):
+for t in range(n_steps):
     vg.step(orders[t])
     vg._L.xr_debug_env_records(vg._h, rec)
     r = np.array(rec[:], np.int64).reshape(n_envs, 8)
@@ -46,7 +48,7 @@ v = [int(x) for x in out]
 names = ["seed+connect", "boxes+push", "classify", "expand", "target", "walk", "commit"]
 nets = max(v[13], 1)
 print(f"{preset} x {n_envs} x {n_nets}: nets {v[13]}, connections {v[10]}, rounds {v[9]} (max per net {v[12]}), expanded entries {v[11]}")
-print(f"kernel cycles per net: mean {v[0] / nets:.0f}, max {v[1]}; CTA 0 (most pins) mean {v[14] / n_nets:.0f} cycles, {v[15] / n_nets:.1f} rounds")
+print(f"kernel cycles per net: mean {v[0] / nets:.0f}, max {v[1]}; CTA 0 (most pins) mean {v[14] / n_steps:.0f} cycles, {v[15] / n_steps:.1f} rounds")
 for k, n in enumerate(names):
     print(f"   {n:14s} {v[2 + k] / nets:10.0f} cycles/net  {100.0 * v[2 + k] / max(v[0], 1):5.1f} %   per connection {v[2 + k] / max(v[10], 1):8.0f}   per round {v[2 + k] / max(v[9], 1):8.0f}")
 vg.close()

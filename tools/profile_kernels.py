@@ -12,7 +12,7 @@ from bench import make_orders, N_NETS, SEED, ENVS_PER_GPU
 geom = preset_geometry("SYN-256")
 insts = make_batch(geom, ENVS_PER_GPU, N_NETS, SEED)
 sched = make_orders(insts, 40, SEED)
-vg = VecGame(geom, insts, device=0)
+vg = VecGame(geom, insts, device=0, metrics_mode=1)
 vg.reset()
 for t in range(16):
     vg.step(sched[t])
