@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define XR_VERSION 1
+#define XR_VERSION 2
 
 #define XR_OK            0
 #define XR_E_INVALID    -1   /* bad argument                                    */
@@ -90,7 +90,12 @@ typedef struct XrConfig {
     int32_t metrics_mode;      /* 0 = blocked / shorted / overflow counts are maintained by the commits (O(path cells));
                                   1 = recomputed by a full scan of the occupancy field every step (the checker, and the
                                   HBM-bound "reward kernel" the roofline is quoted on).  Same results.                  */
-    int32_t reserved[2];
+    int32_t guide_cost;        /* optional cost term (run-net-ordering-training.tcl:3 -follow_guide 1, GUIDECOST 1): both
+                                  multipliers gain + guide_cost on a cell outside every guide box of the net (xr_load_guides);
+                                  0 = off (default).  Frontier engine only.                                             */
+    int32_t halo;              /* optional cost term (SHAPEBLOATWIDTH 3.0): cells within `halo` tracks (same layer) of a routed
+                                  net's wires count as route shapes (DRC cost) for the nets routed later; 0 = off (default),
+                                  at most 8.  Frontier engine only.  No effect on the metrics.                          */
 } XrConfig;
 
 /* cumulative metric slots of xr_step_results / XR_BUF_CUM */
@@ -132,6 +137,11 @@ const char *xr_last_error(const XrEnv *env);   /* env may be NULL: last create e
 int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, const int32_t *block_xyz,
                      int32_t n_ap, const int32_t *ap_net, const int32_t *ap_pin,
                      const int32_t *ap_xyz);
+
+/* Route guides of environment env_id for the optional guide term (XrConfig.guide_cost > 0): boxes [n][6] = net, x0, x1,
+ * y0, y1, z in cells, inclusive (the .guide file of the design, ispd/ispd18_test1/ispd18_test1.input.guide, clipped to
+ * the region).  A net without boxes has no guide term.  Replaces the previous boxes; synchronous.                     */
+int xr_load_guides(XrEnv *env, int32_t env_id, int32_t n_boxes, const int32_t *boxes);
 
 /* Reset environments env_ids[0..k) (NULL = all) to their loaded instance and
  * rebuild their observations.  Asynchronous on `stream`.                        */

@@ -40,6 +40,8 @@ def lib():
         L.orc_load.restype = C.c_int
         L.orc_load.argtypes = [p, C.c_int, i32p, C.c_int, i32p, i32p, i32p]
         L.orc_reset.argtypes = [p]
+        L.orc_set_options.argtypes = [p, C.c_int, C.c_int]
+        L.orc_load_guides.argtypes = [p, C.c_int, i32p]
         L.orc_remaining.restype = C.c_int
         L.orc_remaining.argtypes = [p, i32p]
         L.orc_obs.restype = C.c_int
@@ -80,7 +82,7 @@ def reward(violation: int, wirelength: int, via: int) -> float:
 class OracleEnv:
     """Single-region CPU environment with the oracle's route/commit/metrics/obs."""
 
-    def __init__(self, geom, inst=None):
+    def __init__(self, geom, inst=None, *, guide_cost: int = 0, halo: int = 0):
         L = lib()
         self.geom = geom
         xc, xcp = _i32(geom.x_coords)
@@ -92,6 +94,7 @@ class OracleEnv:
                                pip_, mwp, geom.via_cost, geom.grid_cost, geom.drc_cost,
                                geom.fixed_shape_cost, geom.block_cost)
         self.inst = None
+        L.orc_set_options(self._h, int(guide_cost), int(halo))
         if inst is not None:
             self.load(inst)
 
@@ -111,6 +114,9 @@ class OracleEnv:
         rc = lib().orc_load(self._h, len(inst.block_xyz), bp, len(inst.ap_net), np_, pp, xp)
         if rc != 0:
             raise ValueError(f"orc_load failed: {rc}")
+        g = getattr(inst, "guides", None)
+        gb, gbp = _i32(np.zeros((0, 6), np.int32) if g is None else np.asarray(g, np.int32).reshape(-1, 6))
+        lib().orc_load_guides(self._h, len(gb), gbp)
         self.inst = inst
         self.reset()
 

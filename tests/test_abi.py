@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.load()
     for s in _header_symbols():
         assert hasattr(L, s), s
-    assert L.xr_version() == 1
+    assert L.xr_version() == 2
 
 
 def test_config_struct_layout_matches_header():

@@ -15,7 +15,7 @@ def _run_episode(geom, insts, seed=0, check_obs_every=1, steps=None, **vgkw):
     from xroute_env_b200 import VecGame
     vg = VecGame(geom, insts, device=0, **vgkw)
     vg.reset()
-    oracles = [OracleEnv(geom, i) for i in insts]
+    oracles = [OracleEnv(geom, i, guide_cost=vgkw.get("guide_cost", 0), halo=vgkw.get("halo", 0)) for i in insts]
     rng = np.random.default_rng(seed)
     orders = [list(rng.permutation(i.net_ids)) for i in insts]
     for e, orc in enumerate(oracles):
@@ -89,6 +89,54 @@ def test_frontier_engine_knobs(knobs, monkeypatch):
     geom = ispd18_geometry(90, 70, 9)
     geom.x_coords = np.cumsum(np.random.default_rng(1).integers(100, 700, 90)).astype(np.int32)   # non-uniform pitch
     _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, check_obs_every=4)
+
+
+def _with_guides(geom, insts, margin, layers):
+    """Synthetic route guides: per net the bounding box of its access points grown by `margin` cells, on `layers`."""
+    out = []
+    for inst in insts:
+        boxes = []
+        for n in inst.net_ids:
+            xy = inst.ap_xyz[inst.ap_net == n]
+            x0, y0 = xy[:, 0].min() - margin, xy[:, 1].min() - margin
+            x1, y1 = xy[:, 0].max() + margin, xy[:, 1].max() + margin
+            if n % 5 == 0:
+                continue                                   # some nets come without guides: no guide term for them
+            for z in layers:
+                boxes.append((n, x0, x1, y0, y1, z))
+        inst.guides = np.array(boxes, np.int32).reshape(-1, 6)
+        out.append(inst)
+    return out
+
+
+@pytest.mark.parametrize("kw", [dict(guide_cost=1), dict(guide_cost=4, halo=1), dict(halo=2), dict(guide_cost=1, halo=1, metrics_mode=1)],
+                         ids=["guide1", "guide4-halo1", "halo2", "guide1-halo1-scan"])
+def test_optional_cost_terms_guide_and_halo(kw):
+    """The two optional terms of the pinned run configuration (-follow_guide 1 / GUIDECOST, SHAPEBLOATWIDTH): out-of-guide
+    multiplier and the spacing halo of routed wires, oracle and frontier engine together, bit-exact on congested
+    instances where both change the routes (checked: the same episodes route differently with the terms off)."""
+    from oracle.oracle import OracleEnv
+    geom = ispd18_geometry(40, 36, 6)
+    insts = _with_guides(geom, make_batch(geom, 4, 12, seed=321, p_obstacle=0.2), margin=1, layers=(0, 2))
+    _run_episode(geom, insts, seed=4, check_obs_every=4, **kw)
+    # the terms are not inert: with them off at least one route of the episode differs
+    a, b = OracleEnv(geom, insts[0]), OracleEnv(geom, insts[0], guide_cost=kw.get("guide_cost", 0), halo=kw.get("halo", 0))
+    differs = False
+    for net in insts[0].net_ids:
+        a.step(net); b.step(net)
+        differs |= not np.array_equal(a.last_paths()[0], b.last_paths()[0])
+    assert differs
+    geom = ispd18_geometry(70, 50, 9)
+    geom.x_coords = np.cumsum(np.random.default_rng(2).integers(100, 700, 70)).astype(np.int32)
+    insts = _with_guides(geom, make_batch(geom, 3, 10, seed=322), margin=0, layers=(0, 1, 2, 3))
+    _run_episode(geom, insts, seed=5, check_obs_every=5, **kw)
+
+
+def test_optional_cost_terms_need_the_frontier_engine():
+    from xroute_env_b200 import VecGame
+    geom = ispd18_geometry(20, 20, 3)
+    with pytest.raises(RuntimeError, match="frontier engine"):
+        VecGame(geom, make_batch(geom, 1, 3, seed=1), device=0, engine=1, halo=1)
 
 
 @pytest.mark.parametrize("engine", [0, 1], ids=["frontier", "sweeps"])

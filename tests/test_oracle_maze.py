@@ -224,3 +224,46 @@ def test_goal_directed_partial_field_gives_the_same_routes(seed):
         assert (m["d_wirelength"], m["d_via"]) == (wl, via)
     ou, oown = env.state()
     assert np.array_equal(ou, usage) and np.array_equal(oown, owner)
+
+
+def _one_layer(X, Y, aps, guides=None):
+    from xroute_env_b200.instances import Instance
+    geom = ispd18_geometry(X, Y, 1)                      # one horizontal layer: x step 400, y step 380 (wrong-way: x3)
+    a = np.array(aps, np.int32)
+    inst = Instance(block_xyz=np.zeros((0, 3), np.int32), ap_net=a[:, 0].copy(), ap_pin=a[:, 1].copy(),
+                    ap_xyz=np.ascontiguousarray(a[:, 2:5]))
+    if guides is not None:
+        inst.guides = np.array(guides, np.int32).reshape(-1, 6)
+    return geom, inst
+
+
+def test_guide_term_known_answers():
+    """Hand-made maze for the out-of-guide term (run-net-ordering-training.tcl:3 -follow_guide 1, GUIDECOST): pins at both
+    ends of row 0, the guide runs around through row 2.  Straight: 2 + 3 steps inside the guide (400 each) and 3 outside
+    (400 (1 + GUIDE)); around: 4 x steps inside + 4 inside x steps of the end pieces (400 each) and 4 wrong-way y steps
+    (380 x 3).  GUIDE = 1: straight wins, 8 x 400 + 3 x 400 = 4400.  GUIDE = 20: around wins, 8 x 400 + 4 x 1140 = 7760."""
+    guides = [(1, 0, 2, 0, 0, 0), (1, 2, 2, 0, 2, 0), (1, 2, 6, 2, 2, 0), (1, 6, 6, 0, 2, 0), (1, 6, 8, 0, 0, 0)]
+    geom, inst = _one_layer(9, 5, [(1, 1, 0, 0, 0), (1, 2, 8, 0, 0)], guides)
+    for gcost, want, rows in ((0, 3200, {0}), (1, 4400, {0}), (20, 7760, {0, 1, 2})):
+        env = OracleEnv(geom, inst, guide_cost=gcost)
+        env.step(1)
+        cells, off, cost = env.last_paths()
+        assert cost.tolist() == [want], (gcost, cost)
+        assert {int(c) // 9 for c in cells} == rows, (gcost, cells)
+
+
+def test_halo_term_known_answers():
+    """Hand-made maze for the spacing halo (SHAPEBLOATWIDTH): net 1 runs straight along row 3; net 2 has its pins at both
+    ends of row 2, the track next to it.  Without halo net 2 runs straight (9 x 400 = 3600).  With halo 1 every cell of
+    row 2 counts as route shape (x 9): net 2 drops to row 1 (wrong-way 380 x 3), runs there (9 x 400) and climbs back
+    into the halo at its pin (380 x (1 + 2 + 8)): 1140 + 3600 + 4180 = 8920.  The metrics do not see the halo."""
+    geom, inst = _one_layer(10, 7, [(1, 1, 0, 3, 0), (1, 2, 9, 3, 0), (2, 1, 0, 2, 0), (2, 2, 9, 2, 0)])
+    for halo, want, rows in ((0, 3600, {2}), (1, 8920, {1, 2})):
+        env = OracleEnv(geom, inst, halo=halo)
+        m1 = env.step(1)
+        assert env.last_paths()[2].tolist() == [3600]
+        m2 = env.step(2)
+        cells, off, cost = env.last_paths()
+        assert cost.tolist() == [want], (halo, cost)
+        assert {int(c) // 10 for c in cells} == rows
+        assert (m2["violation"], m2["overflow"]) == (0, 0)

@@ -44,6 +44,17 @@ while time.time() - t0 < budget and not bad:
     # hybrid threshold anywhere from "every net" to "no net" on the sweep kernels; engine 1: the sweep engines alone
     kw["engine"] = int(rng.random() < 0.3)
     kw["metrics_mode"] = int(rng.random() < 0.3)
+    if kw["engine"] == 0 and rng.random() < 0.35:         # the optional cost terms (frontier engine only), with synthetic guides
+        kw["guide_cost"], kw["halo"] = int(rng.choice([0, 1, 4])), int(rng.choice([0, 1, 2]))
+        for inst in insts:
+            boxes = []
+            for n in inst.net_ids:
+                xy = inst.ap_xyz[inst.ap_net == n]
+                m = int(rng.integers(0, 3))
+                for z in range(0, Z, int(rng.integers(1, 3))):
+                    if rng.random() < 0.8:
+                        boxes.append((n, xy[:, 0].min() - m, xy[:, 0].max() + m, xy[:, 1].min() - m, xy[:, 1].max() + m, z))
+            inst.guides = np.array(boxes, np.int32).reshape(-1, 6)
     knobs = {"XR_FR_RAY": str(int(rng.integers(1, 9))), "XR_FR_DELTA": str(int(rng.choice([0, 100, 400, 1200, 100000]))),
              "XR_FR_DMAX": str(int(rng.choice([1, 4, 16]))), "XR_FR_THREADS": str(int(rng.choice([64, 256, 1024]))),
              "XR_HYBRID_AREA": str(int(rng.choice([0, 30, 400, 4000]))), "XR_HYBRID_PINS": str(int(rng.choice([2, 3, 30])))}
@@ -56,7 +67,7 @@ while time.time() - t0 < budget and not bad:
         os.environ[k] = v
     vg = VecGame(geom, insts, device=0, **kw)
     vg.reset()
-    orcs = [OracleEnv(geom, i) for i in insts]
+    orcs = [OracleEnv(geom, i, guide_cost=kw.get("guide_cost", 0), halo=kw.get("halo", 0)) for i in insts]
     orders = [list(rng.permutation(i.net_ids)) for i in insts]
     for t in range(max(len(o) for o in orders)):
         acts = np.array([int(o[t]) if t < len(o) else 0 for o in orders], np.int32)

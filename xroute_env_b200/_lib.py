@@ -36,7 +36,7 @@ class XrConfig(C.Structure):
         ("via_cost", C.c_int32), ("grid_cost", C.c_int32), ("drc_cost", C.c_int32),
         ("fixed_shape_cost", C.c_int32), ("block_cost", C.c_int32),
         ("pumps_per_sync", C.c_int32), ("window_margin", C.c_int32), ("min_cluster", C.c_int32),
-        ("obs_mode", C.c_int32), ("engine", C.c_int32), ("metrics_mode", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("obs_mode", C.c_int32), ("engine", C.c_int32), ("metrics_mode", C.c_int32), ("guide_cost", C.c_int32), ("halo", C.c_int32),
     ]
 
 
@@ -52,7 +52,7 @@ class IllegalAction(XrError):
 
 # every symbol include/xroute_b200.h declares (tests/test_abi.py checks the two agree)
 SYMBOLS = [
-    "xr_version", "xr_create", "xr_destroy", "xr_last_error", "xr_load_instance", "xr_reset",
+    "xr_version", "xr_create", "xr_destroy", "xr_last_error", "xr_load_instance", "xr_load_guides", "xr_reset",
     "xr_step", "xr_step_async", "xr_step_wait", "xr_step_results", "xr_obs_layout", "xr_obs_channels", "xr_obs_copy",
     "xr_obs_dlpack", "xr_buffer_dlpack", "xr_buffer_ptr", "xr_legal_mask", "xr_get_paths",
     "xr_get_state", "xr_get_dist", "xr_stats_update", "xr_counters", "xr_profile_enable",
@@ -84,6 +84,8 @@ def load():
     L.xr_last_error.argtypes = [vp]
     L.xr_load_instance.restype = C.c_int
     L.xr_load_instance.argtypes = [vp, C.c_int32, C.c_int32, i32p, C.c_int32, i32p, i32p, i32p]
+    L.xr_load_guides.restype = C.c_int
+    L.xr_load_guides.argtypes = [vp, C.c_int32, C.c_int32, i32p]
     L.xr_reset.restype = C.c_int
     L.xr_reset.argtypes = [vp, i32p, C.c_int32, vp]
     L.xr_step.restype = C.c_int

@@ -72,6 +72,7 @@ struct XrEnv {
     int fr_threads_big = FR_T, fr_threads_small = 512;
     int hybrid_area = 4000, hybrid_pins = 3;   // hybrid: nets of at most hybrid_pins pins whose access-point box covers at least hybrid_area cells take the sweep kernels (0 = never)
     std::vector<int32_t> h_area;        // [N][max_nets+1] cells of the net's access-point bounding box (x by y)
+    int guide_cap = 0;                  // guide boxes per environment the device table holds (grown on demand)
     int metrics_mode = 0;               // 0 = congestion counts maintained by the commits, 1 = full scan (k_metrics) every step
     // counters
     long long n_launch = 0, n_sync = 0;
@@ -366,10 +367,17 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     }
     cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&env->ev_done, cudaEventDisableTiming);
+    g.guide_cost = std::max(0, cfg->guide_cost); g.halo = std::max(0, std::min(8, cfg->halo));
+    env->g.guide_cap = 0;
     env->engine = cfg->engine == 1 ? 1 : 0;
     if (const char *e = getenv("XR_ENGINE")) env->engine = atoi(e) == 1 ? 1 : 0;
+    if ((g.guide_cost > 0 || g.halo > 0) && env->engine == 1) {
+        xr_free(env);
+        return fail(nullptr, XR_E_INVALID, "guide_cost / halo are implemented by the frontier engine only (engine 0)");
+    }
+    if (g.guide_cost > 0 || g.halo > 0) env->hybrid_area = 0;      // every net on the frontier engine
     env->metrics_mode = cfg->metrics_mode == 1 ? 1 : 0;
-    if (const char *e = getenv("XR_HYBRID_AREA")) env->hybrid_area = std::max(0, atoi(e));
+    if (const char *e = getenv("XR_HYBRID_AREA")) if (g.guide_cost == 0 && g.halo == 0) env->hybrid_area = std::max(0, atoi(e));
     if (const char *e = getenv("XR_HYBRID_PINS")) env->hybrid_pins = std::max(2, atoi(e));
     if (const char *e = getenv("XR_METRICS_MODE")) env->metrics_mode = atoi(e) == 1 ? 1 : 0;
     ce = xr_frontier_init(env->smem_cap);
@@ -551,6 +559,53 @@ extern "C" int xr_load_instance(XrEnv *env, int32_t env_id, int32_t n_block, con
     env->h_loaded[env_id] = 1;
     env->h_reset[env_id] = 0;
     env->h_clean[env_id] = 0;            // the access points changed: the next reset rebuilds the observation
+    return XR_OK;
+}
+
+// Route guides of environment env_id (optional cost term, XrConfig.guide_cost): boxes [n][6] = net, x0, x1, y0, y1, z in
+// cells, inclusive.  Replaces the environment's previous boxes.  Synchronous.
+extern "C" int xr_load_guides(XrEnv *env, int32_t env_id, int32_t n_boxes, const int32_t *boxes) {
+    if (!env || env_id < 0 || env_id >= env->g.N || n_boxes < 0 || (n_boxes && !boxes)) return XR_E_INVALID;
+    if (env->pend.active) { const int rc__ = xr_step_wait(env); if (rc__ != XR_OK) return rc__; }
+    Geo &g = env->g;
+    cudaSetDevice(env->device);
+    CK(cudaDeviceSynchronize());
+    if (n_boxes > g.guide_cap || !env->d.guide_box) {               // grow the device table, keeping the other environments' boxes
+        const int cap = std::max(std::max(n_boxes, 256), 2 * g.guide_cap);
+        int32_t *nb = nullptr, *ns = env->d.guide_start;
+        CK(cudaMalloc(&nb, sizeof(int32_t) * 5 * (size_t)cap * g.N));
+        CK(cudaMemset(nb, 0, sizeof(int32_t) * 5 * (size_t)cap * g.N));
+        if (!ns) {
+            CK(cudaMalloc(&ns, sizeof(int32_t) * (size_t)(g.max_nets + 2) * g.N));
+            CK(cudaMemset(ns, 0, sizeof(int32_t) * (size_t)(g.max_nets + 2) * g.N));
+            env->allocs.push_back(ns);
+            env->d.guide_start = ns;
+        }
+        if (env->d.guide_box) {
+            for (int e = 0; e < g.N; e++)
+                CK(cudaMemcpy(nb + (size_t)e * cap * 5, env->d.guide_box + (size_t)e * g.guide_cap * 5, sizeof(int32_t) * 5 * g.guide_cap, cudaMemcpyDeviceToDevice));
+            env->allocs.erase(std::find(env->allocs.begin(), env->allocs.end(), (void *)env->d.guide_box));
+            cudaFree(env->d.guide_box);
+        }
+        env->allocs.push_back(nb);
+        env->d.guide_box = nb;
+        g.guide_cap = cap;
+    }
+    std::vector<int> order(n_boxes);
+    for (int i = 0; i < n_boxes; i++) {
+        order[i] = i;
+        if (boxes[6 * i] < 1 || boxes[6 * i] > g.max_nets) return fail(env, XR_E_INVALID, "guide box of a net outside 1..max_nets");
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return boxes[6 * a] < boxes[6 * b]; });
+    std::vector<int32_t> start(g.max_nets + 2, 0), box((size_t)std::max(n_boxes, 1) * 5, 0);
+    for (int k = 0; k < n_boxes; k++) {
+        const int32_t *b = boxes + 6 * order[k];
+        start[b[0] + 1]++;
+        for (int j = 0; j < 5; j++) box[5 * (size_t)k + j] = b[1 + j];
+    }
+    for (int n = 1; n <= g.max_nets + 1; n++) start[n] += start[n - 1];
+    CK(cudaMemcpy(env->d.guide_start + (size_t)env_id * (g.max_nets + 2), start.data(), sizeof(int32_t) * (g.max_nets + 2), cudaMemcpyHostToDevice));
+    if (n_boxes) CK(cudaMemcpy(env->d.guide_box + (size_t)env_id * g.guide_cap * 5, box.data(), sizeof(int32_t) * 5 * n_boxes, cudaMemcpyHostToDevice));
     return XR_OK;
 }
 
@@ -787,6 +842,8 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
                     continue;
                 }
             }
+            if (env->engine == 0 && (g.guide_cost > 0 || g.halo > 0))
+                return fail(env, XR_E_CAPACITY, "a net exceeds the frontier engine's tables (1024 access points / 264 pins), which guide_cost / halo require");
             if (WX > 0 && env->dual_pins > 0 && np >= env->dual_pins && WX < 1024 && WY < 1024 &&
                 env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= WIN_TGT_CAP) {
                 for (int b = NB_BAND; b < XR_NB && bucket < 0; b++) {

@@ -28,23 +28,28 @@
 #define CF_FS   2u   // access point of another net (fixed-shape cost)
 #define CF_BLK  4u   // blockage
 #define CF_TREE 8u   // cell belongs to the tree of the net being routed
+#define CF_OG  16u   // outside every guide box of the net being routed (frontier engine, XrConfig.guide_cost)
 
 // Frontier cell word (64 bit, one per cell): everything a relaxation needs in ONE load.
-//   [63:34] ~epoch (30 bits)  a word of an older epoch reads as distance = infinity; all ones = older than any epoch
-//   [33:4]  distance (30 bits, XR_INF = all ones)
-//   [3] access point of the net being routed (set by the frontier kernel for the duration of the net)
-//   [2] access point of some net   [1] blockage   [0] a committed wire covers the cell
+//   [63:35] ~epoch (29 bits)  a word of an older epoch reads as distance = infinity; all ones = older than any epoch
+//   [34:5]  distance (30 bits, XR_INF = all ones)
+//   [4] inside a guide box of the net being routed   [3] access point of the net being routed
+//       (both set by the frontier kernel for the duration of the net)
+//   [2] access point of some net   [1] blockage   [0] route shape: a committed wire covers the cell, or the cell lies in
+//       the spacing halo of one (XrConfig.halo)
 // atomicMin on the whole word relaxes the cell (newer epoch and smaller distance both compare smaller; the flag bits of
 // a cell are the same in every candidate value).
 #define FRW_RS  1ull
 #define FRW_BLK 2ull
 #define FRW_AP  4ull
 #define FRW_OWN 8ull
-#define FRW_FLAGS 15ull
-#define FRW_STALE 0xFFFFFFFFFFFFFFF0ull
-#define FRW_EPOCH_MASK 0x3FFFFFFFu
-__host__ __device__ inline unsigned long long frw_make(uint32_t hi30, uint32_t dist, uint32_t flags) {
-    return ((unsigned long long)hi30 << 34) | ((unsigned long long)dist << 4) | flags;
+#define FRW_GUIDE 16ull
+#define FRW_FLAGS 31ull
+#define FRW_SHIFT 5
+#define FRW_STALE 0xFFFFFFFFFFFFFFE0ull
+#define FRW_EPOCH_MASK 0x1FFFFFFFu
+__host__ __device__ inline unsigned long long frw_make(uint32_t hi29, uint32_t dist, uint32_t flags) {
+    return ((unsigned long long)hi29 << (FRW_SHIFT + 30)) | ((unsigned long long)dist << FRW_SHIFT) | flags;
 }
 
 struct Geo {
@@ -55,6 +60,7 @@ struct Geo {
     int max_nets, max_aps, obs_max_nets, path_cap, conn_cap;
     long long obs_stride;   // floats per environment
     int uniform_x, uniform_y, dx, dy;
+    int guide_cost, halo, guide_cap;   // optional cost terms (XrConfig.guide_cost / halo); boxes per environment
     const int32_t *xc, *yc; // device copies of the track coordinates
     uint32_t multX[XR_ZMAX][4];  // 1 + GRID*[layer not horizontal] + DRC*rs + FIXED*fs
     uint32_t multY[XR_ZMAX][4];
@@ -119,6 +125,8 @@ struct Dev {
     uint32_t *fr_epoch;           // [N] epoch of the last connection searched
     uint32_t *fr_spill;           // [N][4*cap_g + 2*cap_ge] open-list / expansion-list entries beyond the shared-memory part
     long long *minc;              // [N][4] blocked, shorted, overflow maintained by the commits (checked against k_metrics)
+    int32_t *guide_start;         // [N][max_nets+2] guide boxes of net k: guide_box[guide_start[k] .. guide_start[k+1])
+    int32_t *guide_box;           // [N][guide_cap][5] x0, x1, y0, y1, z (cells, inclusive)
     // last routed paths (parity / debug)
     int32_t  *path;       // [N][path_cap] canonical indices
     int32_t  *path_n;     // [N]

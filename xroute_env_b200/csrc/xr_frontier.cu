@@ -140,6 +140,25 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
     }
     const size_t eoff = (size_t)env * g.cells_p;
     unsigned long long *dist = d.dist64 + eoff;
+    // optional cost term: cells inside the net's guide boxes are marked for the duration of the kernel (a net without
+    // boxes has no guide term)
+    const uint32_t gcost = (uint32_t)g.guide_cost;
+    int gb0 = 0, gb1 = 0;
+    if (g.guide_cost > 0) { const int *gs = d.guide_start + (size_t)env * (g.max_nets + 2); gb0 = gs[net]; gb1 = gs[net + 1]; }
+    const bool has_guides = gb1 > gb0;
+    auto guide_marks = [&](bool set) {
+        for (int b = gb0; b < gb1; b++) {
+            const int *q = d.guide_box + ((size_t)env * g.guide_cap + b) * 5;
+            const int x0 = max(q[0], 0), x1 = min(q[1], X - 1), y0 = max(q[2], 0), y1 = min(q[3], Y - 1), z = q[4];
+            if (z < 0 || z >= Z || x1 < x0 || y1 < y0) continue;
+            const int w = x1 - x0 + 1, n = w * (y1 - y0 + 1);
+            for (int i = tid; i < n; i += T) {
+                unsigned long long *p = dist + ((size_t)z * Y + y0 + i / w) * Xp + x0 + i % w;
+                if (set) atomicOr(p, FRW_GUIDE); else atomicAnd(p, ~FRW_GUIDE);
+            }
+        }
+    };
+    guide_marks(true);
     const uint32_t *cinfo = d.cellinfo + eoff;
     const uint16_t *apn = d.apnet + eoff;
     int *path = d.path + (size_t)env * g.path_cap;
@@ -189,23 +208,25 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
     // weight of the move p -> c = p + delta(dir), f = flags of c, from the shared-memory tables
     auto mw = [&](int px, int py, int pz, int dir, uint32_t f) -> uint32_t {
         uint32_t w;
-        if (dir < 2) w = lenx(px, dir == 0 ? px + 1 : px - 1) * s_mx[4 * pz + (f & 3u)] + ((f & CF_BLK) ? s_pen[pz] : 0u);
-        else if (dir < 4) w = leny(py, dir == 2 ? py + 1 : py - 1) * s_my[4 * pz + (f & 3u)] + ((f & CF_BLK) ? s_pen[pz] : 0u);
-        else if (dir == 4) w = s_vlen[pz] * s_mv[f & 3u] + ((f & CF_BLK) ? s_pen[pz + 1] : 0u);
-        else w = s_vlen[pz - 1] * s_mv[f & 3u] + ((f & CF_BLK) ? s_pen[pz - 1] : 0u);
+        const uint32_t og = (f & CF_OG) ? gcost : 0u;
+        if (dir < 2) w = lenx(px, dir == 0 ? px + 1 : px - 1) * (s_mx[4 * pz + (f & 3u)] + og) + ((f & CF_BLK) ? s_pen[pz] : 0u);
+        else if (dir < 4) w = leny(py, dir == 2 ? py + 1 : py - 1) * (s_my[4 * pz + (f & 3u)] + og) + ((f & CF_BLK) ? s_pen[pz] : 0u);
+        else if (dir == 4) w = s_vlen[pz] * (s_mv[f & 3u] + og) + ((f & CF_BLK) ? s_pen[pz + 1] : 0u);
+        else w = s_vlen[pz - 1] * (s_mv[f & 3u] + og) + ((f & CF_BLK) ? s_pen[pz - 1] : 0u);
         return w;
     };
     // cost flags (CF_*) of a cell for this net from its word alone (the net's own access points carry FRW_OWN while it
     // is routed).  Sets own = the cell is an access point of this net.
     auto wflags = [&](unsigned long long w, size_t idx, bool &own) -> uint32_t {
         own = (w & FRW_OWN) != 0ull;
-        return (uint32_t)(w & FRW_RS) | (uint32_t)((w & FRW_BLK) << 1) | (((w & (FRW_AP | FRW_OWN)) == FRW_AP) ? CF_FS : 0u);
+        return (uint32_t)(w & FRW_RS) | (uint32_t)((w & FRW_BLK) << 1) | (((w & (FRW_AP | FRW_OWN)) == FRW_AP) ? CF_FS : 0u) |
+               ((has_guides && !(w & FRW_GUIDE)) ? CF_OG : 0u);
     };
 
     for (;;) {                                           // ---- one connection per trip
         epoch++;
         const uint32_t hi = (~epoch) & FRW_EPOCH_MASK;
-        auto dval = [&](unsigned long long v) -> uint32_t { return (uint32_t)(v >> 34) == hi ? ((uint32_t)(v >> 4) & 0x3FFFFFFFu) : XR_INF; };
+        auto dval = [&](unsigned long long v) -> uint32_t { return (uint32_t)(v >> (FRW_SHIFT + 30)) == hi ? ((uint32_t)(v >> FRW_SHIFT) & 0x3FFFFFFFu) : XR_INF; };
         if (tid == 0) {
             S->cnt[0] = 0; S->cnt[1] = 0; S->fmin[0] = 0xFFFFFFFFu; S->fmin[1] = 0xFFFFFFFFu;
             S->nexp[0] = 0; S->nexp[1] = 0; S->nray[0] = 0; S->nray[1] = 0; S->B = XR_INF; S->nbox = 0; S->best = ~0ull; S->dmul = 1;
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
         // ---- pins the tree touches are connected (any access point on the tree)
         if (!first) {
             for (int i = tid; i < n_ap; i += T)
-                s_apon[i] = s_apconn[i] ? 1 : ((__ldcg(dist + s_apcp[i]) >> 4) == ((unsigned long long)hi << 30));
+                s_apon[i] = s_apconn[i] ? 1 : ((__ldcg(dist + s_apcp[i]) >> FRW_SHIFT) == ((unsigned long long)hi << 30));
             __syncthreads();
             for (int i = tid; i < n_ap; i += T) {
                 if (s_apconn[i]) continue;
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 if (valid) {
                     const uint32_t f = wflags(wv, idx, isown);
                     const uint32_t len = alongx ? lenx(xv, xv - sgn) : leny(yv, yv - sgn);
-                    wgt = len * (alongx ? s_mx : s_my)[4 * z + (f & 3u)] + ((f & CF_BLK) ? s_pen[z] : 0u);
+                    wgt = len * ((alongx ? s_mx : s_my)[4 * z + (f & 3u)] + ((f & CF_OG) ? gcost : 0u)) + ((f & CF_BLK) ? s_pen[z] : 0u);
                 }
 #pragma unroll
                 for (int off = 1; off < FR_RAY; off <<= 1) {          // inclusive prefix sum inside the 8-lane group
@@ -462,8 +483,9 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 if (valid) {
                     const uint32_t f = wflags(wv, idx, isown);
                     uint32_t wgt;
-                    if (j < 2) wgt = (alongx ? leny(yv, y) : lenx(xv, x)) * (alongx ? s_my : s_mx)[4 * z + (f & 3u)];
-                    else wgt = s_vlen[j == 2 ? z : z - 1] * s_mv[f & 3u];
+                    const uint32_t og = (f & CF_OG) ? gcost : 0u;
+                    if (j < 2) wgt = (alongx ? leny(yv, y) : lenx(xv, x)) * ((alongx ? s_my : s_mx)[4 * z + (f & 3u)] + og);
+                    else wgt = s_vlen[j == 2 ? z : z - 1] * (s_mv[f & 3u] + og);
                     nd = d0 + wgt + ((f & CF_BLK) ? s_pen[zv] : 0u);
                 }
                 const uint32_t Bnow = *(volatile uint32_t *)&S->B;
@@ -631,6 +653,16 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
     // ---- write back
     __syncthreads();
     for (int i = tid; i < n_ap; i += T) atomicAnd(dist + s_apcp[i], ~FRW_OWN);
+    guide_marks(false);
+    if (g.halo > 0 && !S->walk_fail && !S->err) {
+        // optional cost term: the spacing halo of this net's wires counts as route shape for the nets routed later
+        const int hw = 2 * g.halo + 1;
+        for (int i = tid; i < pn * hw * hw; i += T) {
+            const int ci = __ldcg(path + i / (hw * hw)), r = i % (hw * hw);
+            const int x = ci % X + r % hw - g.halo, y = (ci / X) % Y + r / hw - g.halo, z = ci / (X * Y);
+            if (x >= 0 && x < X && y >= 0 && y < Y) atomicOr(dist + ((size_t)z * Y + y) * Xp + x, FRW_RS);
+        }
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         work += __shfl_xor_sync(0xFFFFFFFFu, work, off);

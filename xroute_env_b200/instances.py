@@ -92,6 +92,7 @@ class Instance:
     ap_pin: np.ndarray                    # int32 [n_ap]  1-based pin id inside the net
     ap_xyz: np.ndarray                    # int32 [n_ap, 3]
     meta: dict = field(default_factory=dict)
+    guides: np.ndarray | None = None      # int32 [n, 6] net, x0, x1, y0, y1, z (cells, inclusive): route guides (optional)
 
     @property
     def net_ids(self) -> list[int]:

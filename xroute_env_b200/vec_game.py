@@ -27,7 +27,7 @@ class VecGame:
                  max_nets: int | None = None, max_aps: int | None = None,
                  obs_max_nets: int = -1, path_capacity: int = 0, pumps_per_sync: int = 0,
                  window_margin: int = 0, min_cluster: int = 0, obs_mode: int = 0, engine: int = 0,
-                 metrics_mode: int = 0):
+                 metrics_mode: int = 0, guide_cost: int = 0, halo: int = 0):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.geom = geom
@@ -57,6 +57,8 @@ class VecGame:
         cfg.window_margin, cfg.min_cluster = window_margin, min_cluster
         cfg.obs_mode = obs_mode
         cfg.engine, cfg.metrics_mode = engine, metrics_mode
+        cfg.guide_cost, cfg.halo = guide_cost, halo
+        self.guide_cost = guide_cost
         rc = self._L.xr_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()
@@ -99,6 +101,10 @@ class VecGame:
         x = np.ascontiguousarray(inst.ap_xyz, np.int32).reshape(-1)
         _lib.check(self._L.xr_load_instance(self._h, env_id, len(b) // 3, _i32p(b), len(n), _i32p(n), _i32p(p),
                                             _i32p(x)), self._h)
+        if self.guide_cost > 0:                      # route guides of the instance (optional cost term)
+            gd = getattr(inst, "guides", None)
+            gb = np.ascontiguousarray(np.zeros((0, 6), np.int32) if gd is None else gd, np.int32).reshape(-1, 6)
+            _lib.check(self._L.xr_load_guides(self._h, env_id, len(gb), _i32p(gb)), self._h)
 
     # ----------------------------------------------------------------- reset/step
     def reset(self, env_ids=None):
