@@ -588,6 +588,19 @@ def test_real_ispd18_test1_regions(name):
     _run_episode(g, [inst, inst], seed=17, check_obs_every=5)
 
 
+@pytest.mark.parametrize("name", ["t1_7x7_y79800", "t1_7x7_y319200", "t1_1x1_gx3_gy6"])
+def test_real_regions_with_the_pinned_guide_and_halo_terms(name):
+    """The real ispd18_test1 regions with their real route guides (ispd18_test1.input.guide clipped to the region) under
+    the run configuration the reference pins (-follow_guide 1, GUIDECOST 1, SHAPEBLOATWIDTH -> one track of halo):
+    frontier engine == oracle, bit-exact."""
+    import os
+    from xroute_env_b200.ispd import load_regions
+    g, inst = load_regions(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                        "ispd18_test1_regions.npz"))[name]
+    assert inst.guides is not None and len(inst.guides) > 0
+    _run_episode(g, [inst, inst], seed=23, check_obs_every=6, guide_cost=1, halo=1)
+
+
 def test_stop_idle_single_pin_and_state_errors():
     """Protocol edge cases of net_ordering.proto: -1 stops an environment (:48), 0 leaves it untouched, a net with
     a single pin is only marked routed (nothing to connect), stepping before the first reset is an error."""

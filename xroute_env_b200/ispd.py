@@ -418,12 +418,25 @@ def extract_region(design: Design, route_box, *, ext: int = 2000, max_aps_per_pi
     ap_xyz = np.asarray(ap_xyz, np.int32).reshape(-1, 3)
     if len(ap_xyz):
         block[ap_xyz[:, 2], ap_xyz[:, 1], ap_xyz[:, 0]] = False
+    # ---- route guides of the kept nets, in cells (optional guide term of the router, XrConfig.guide_cost): the tracks
+    # whose coordinate lies inside a guide rectangle, on the rectangle's layer
+    gboxes = []
+    for nid, nname in enumerate(kept, 1):
+        for (x0, y0, x1, y1, layer) in design.guides.get(nname, ()):
+            z = lef.layer_index(layer)
+            if z < 0:
+                continue
+            i0, i1 = int(np.searchsorted(xc, x0, "left")), int(np.searchsorted(xc, x1, "right")) - 1
+            j0, j1 = int(np.searchsorted(yc, y0, "left")), int(np.searchsorted(yc, y1, "right")) - 1
+            if i1 >= i0 and j1 >= j0:
+                gboxes.append((nid, i0, i1, j0, j1, z))
     bz, by, bx = np.nonzero(block)
     inst = Instance(
         block_xyz=np.stack([bx, by, bz], 1).astype(np.int32).reshape(-1, 3),
         ap_net=np.asarray(ap_net, np.int32), ap_pin=np.asarray(ap_pin, np.int32), ap_xyz=ap_xyz,
         meta={"route_box": tuple(int(v) for v in route_box), "ext": ext, "net_names": kept,
               "union_tracks": union_tracks},
+        guides=np.asarray(gboxes, np.int32).reshape(-1, 6),
     )
     return geom, inst
 
@@ -440,6 +453,8 @@ def save_regions(path: str, regions: dict) -> None:
         out[f"{name}/block_xyz"] = inst.block_xyz; out[f"{name}/ap_net"] = inst.ap_net
         out[f"{name}/ap_pin"] = inst.ap_pin; out[f"{name}/ap_xyz"] = inst.ap_xyz
         out[f"{name}/route_box"] = np.asarray(inst.meta.get("route_box", (0, 0, 0, 0)), np.int64)
+        if inst.guides is not None:
+            out[f"{name}/guides"] = np.asarray(inst.guides, np.int32).reshape(-1, 6)
     np.savez_compressed(path, **out)
 
 
@@ -453,6 +468,7 @@ def load_regions(path: str) -> dict:
                      layer_dir=z[f"{n}/layer_dir"], layer_pitch=z[f"{n}/layer_pitch"],
                      layer_min_width=z[f"{n}/layer_min_width"])
         inst = Instance(block_xyz=z[f"{n}/block_xyz"], ap_net=z[f"{n}/ap_net"], ap_pin=z[f"{n}/ap_pin"],
-                        ap_xyz=z[f"{n}/ap_xyz"], meta={"route_box": tuple(int(v) for v in z[f"{n}/route_box"])})
+                        ap_xyz=z[f"{n}/ap_xyz"], meta={"route_box": tuple(int(v) for v in z[f"{n}/route_box"])},
+                        guides=z[f"{n}/guides"] if f"{n}/guides" in z.files else None)
         regions[n] = (g, inst)
     return regions
