@@ -633,6 +633,18 @@ def run_ours(args):
                                         "materialised for obstacle + order + the first 8 nets (the full one is 34 GB per environment); 32 steps")
     if rank == 0 and world == 1 and not args.no_ispd:
         ispd = ispd_leg(local, cpu=not args.no_cpu)
+    # BASELINE.json configs[4] with an agent in the loop: the reference's RepresentationNetwork, batched over nets and
+    # environments (xroute_env_b200/agent.py, plain PyTorch), scoring 1024 GPU environments through DLPack
+    rollout = None
+    if rank == 0 and world == 1 and not args.no_legs:
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "ppo_rollout.py"), "--envs", "1024", "--nets", "16",
+                                  "--steps", "48", "--json"], capture_output=True, text=True, timeout=600)
+            rollout = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            rollout["note"] = ("PPO-style rollout: policy (batched reference RepresentationNetwork + heads, eager PyTorch) and environment "
+                               "step alternate on one stream; the split shows which of the two bounds configs[4]")
+        except Exception as ex:
+            rollout = {"error": repr(ex)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -682,6 +694,7 @@ def run_ours(args):
             "metrics_scan": metrics_scan,
             "legs": legs,
             "ispd18_test1": ispd,
+            "ppo_rollout": rollout,
             "route_paths": route_paths,
             "episode_stats": stats,
         }

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--nets", type=int, default=16)
     ap.add_argument("--preset", default="T1-1x1")
     ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--json", action="store_true", help="print one JSON line (used by bench.py)")
     args = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -65,8 +66,9 @@ def main():
     policy = NetScorer().cuda().eval()
     env.reset()
     obs = env.obs_batch()                       # zero-copy, stays valid (updated in place) across steps
-    rank_ids = torch.from_dlpack  # noqa: F841  (all views below come through DLPack as well)
     buf_logp, buf_val, buf_rew, buf_done = [], [], [], []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ms_policy = ms_env = 0.0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     env_steps = 0
@@ -77,6 +79,7 @@ def main():
             if not bool(live.any()):
                 env.reset()
                 continue
+            ev[0].record()
             logits, value = policy(obs, n_rem, args.nets)
             logits[~live] = 0.0                  # finished environments idle (action 0)
             dist = torch.distributions.Categorical(logits=logits)
@@ -85,7 +88,11 @@ def main():
             order = obs[:, 1].flatten(1)[:, :args.nets]
             net_id = order.gather(1, pick[:, None]).squeeze(1).to(torch.int32)
             actions = torch.where(live, net_id, torch.zeros_like(net_id))
+            ev[1].record()
             env.step(actions.cpu())              # N x 4 bytes to the host, the rest stays on the GPU
+            ev[2].record()
+            ev[2].synchronize()
+            ms_policy += ev[0].elapsed_time(ev[1]); ms_env += ev[1].elapsed_time(ev[2])
             buf_logp.append(dist.log_prob(pick)); buf_val.append(value)
             buf_rew.append(env.reward.clone()); buf_done.append(env.done.clone())
             env_steps += int(live.sum())
@@ -93,7 +100,13 @@ def main():
     dt = time.perf_counter() - t0
     stats = allreduce_stats(env.stats())
     rew = torch.stack(buf_rew)
-    if rank == 0:
+    if rank == 0 and args.json:
+        import json
+        print(json.dumps({"grid": f"{args.preset} {geom.X}x{geom.Y}x{geom.Z}", "envs_per_gpu": args.envs, "n_gpus": world, "nets_per_env": args.nets,
+                          "steps": args.steps, "value": env_steps * world / dt, "unit": "env-steps/s incl. policy",
+                          "ms_policy_per_step": ms_policy / max(1, args.steps), "ms_env_per_step": ms_env / max(1, args.steps),
+                          "policy_share": ms_policy / max(ms_policy + ms_env, 1e-9), "episodes_finished": stats["episodes"]}))
+    elif rank == 0:
         print(f"{args.preset} {geom.X}x{geom.Y}x{geom.Z}: {args.envs} envs/GPU x {world} GPU, {args.nets} nets, "
               f"{args.steps} policy+env steps in {dt:.2f}s -> {env_steps * world / dt:.0f} env-steps/s incl. policy; "
               f"mean step reward {rew.mean().item():.1f}; episodes finished {stats['episodes']}")

@@ -641,3 +641,69 @@ def test_stop_idle_single_pin_and_state_errors():
     vg.reset([2])
     assert vg.legal_set(2) == {1, 2, 3} and not int(vg.done.cpu()[2])
     vg.close()
+
+
+def test_gym_style_front_ends():
+    """gymnasium calling convention on Game / VecGame (xroute_env_b200.gym_env): 5-tuple steps, rewards of the reference's
+    scalarisation, auto-reset of finished environments in the vector form."""
+    import torch
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200.gym_env import OrderingTrainingEnv, OrderingTrainingVecEnv
+    geom = ispd18_geometry(25, 26, 9)
+    insts = make_batch(geom, 3, 4, seed=61)
+    env = OrderingTrainingEnv(geometry=geom, instances=[insts[0]])
+    obs, info = env.reset(seed=0)
+    orc = OracleEnv(geom, insts[0])
+    assert info["legal_actions"] == insts[0].net_ids and np.array_equal(obs.numpy(), orc.obs())
+    for k, net in enumerate(insts[0].net_ids):
+        obs, rew, term, trunc, info = env.step(net)
+        m = orc.step(net)
+        assert rew == -(500 * m["d_violation"] + 4 * m["d_via"] + 0.5 * m["d_wirelength"]) and not trunc
+        assert term == (k == 3) and np.array_equal(obs.numpy(), orc.obs())
+    env.close()
+    venv = OrderingTrainingVecEnv(geom, insts)
+    obs, info = venv.reset()
+    assert obs.is_cuda and obs.shape[0] == 3 and info["n_remaining"].tolist() == [4, 4, 4]
+    for net in (1, 2, 3, 4):
+        obs, rew, term, trunc, info = venv.step(np.array([net] * 3, np.int32))
+    assert term.all() and not trunc.any()
+    obs, rew, term, trunc, info = venv.step(np.array([1, 1, 1], np.int32))      # finished environments are reset, action ignored
+    assert info["n_remaining"].tolist() == [4, 4, 4] and not term.any() and float(rew.abs().sum()) == 0.0
+    venv.close()
+
+
+def test_batched_agent_front_end_on_the_gpu():
+    """Row f4: BatchedRepresentationNetwork on CUDA, reading the DLPack observation block of a VecGame mid-episode, against
+    the same module on the CPU fed with the oracle's observations (which tests/test_agent_frontend.py ties to the
+    reference's own RepresentationNetwork).  Float32 convolutions: tolerance 1e-4 absolute / 1e-3 relative."""
+    import torch
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    from xroute_env_b200.agent import BatchedRepresentationNetwork
+    torch.manual_seed(3)
+    geom = ispd18_geometry(30, 28, 9)
+    insts = make_batch(geom, 4, 6, seed=77)
+    vg = VecGame(geom, insts, device=0)
+    vg.reset()
+    orcs = [OracleEnv(geom, i) for i in insts]
+    for net in (2, 5):
+        vg.step(np.array([net] * 4, np.int32))
+        for o in orcs:
+            o.step(net)
+    net_cpu = BatchedRepresentationNetwork().eval()
+    net_gpu = BatchedRepresentationNetwork().eval()
+    net_gpu.load_state_dict(net_cpu.state_dict())
+    net_gpu = net_gpu.cuda()
+    n_rem = vg.n_remaining.clone()
+    with torch.no_grad():
+        ob_g, rep_g, valid_g = net_gpu(vg.obs_batch()[:, :2 + 7 * 6], n_rem)
+    obs = [o.obs()[0] for o in orcs]
+    batch = np.zeros((4, 2 + 7 * 6) + obs[0].shape[1:], np.float32)
+    for k, o in enumerate(obs):
+        batch[k, : o.shape[0]] = o
+    with torch.no_grad():
+        ob_c, rep_c, valid_c = net_cpu(torch.from_numpy(batch), n_rem.cpu())
+    assert torch.equal(valid_g.cpu(), valid_c) and int(valid_c.sum()) == 16
+    assert torch.allclose(ob_g.cpu(), ob_c, atol=1e-4, rtol=1e-3)
+    assert torch.allclose(rep_g.cpu(), rep_c, atol=1e-4, rtol=1e-3)
+    vg.close()

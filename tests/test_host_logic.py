@@ -53,3 +53,31 @@ def test_export_data_layout():
 
 def test_presets():
     assert PRESETS["T1-7x7"] == (112, 116, 9) and PRESETS["SYN-256"] == (256, 256, 9)
+
+
+def test_gym_front_end_registers_under_the_reference_id(monkeypatch):
+    """xroute_env/__init__.py:3-6 registers "xroute_env/ordering-training-v0"; the wrapper does the same when gymnasium
+    is importable (a stub stands in here) and says so clearly when it is not."""
+    import importlib, sys, types
+    import pytest
+    from xroute_env_b200 import gym_env
+    if gym_env._gym is None:
+        with pytest.raises(ImportError, match="gymnasium"):
+            gym_env.register()
+    reg = {}
+    gym = types.ModuleType("gymnasium"); gym.Env = object
+    envs = types.ModuleType("gymnasium.envs"); regm = types.ModuleType("gymnasium.envs.registration")
+    regm.registry = reg
+    regm.register = lambda id, entry_point: reg.__setitem__(id, entry_point)
+    monkeypatch.setitem(sys.modules, "gymnasium", gym)
+    monkeypatch.setitem(sys.modules, "gymnasium.envs", envs)
+    monkeypatch.setitem(sys.modules, "gymnasium.envs.registration", regm)
+    mod = importlib.reload(gym_env)
+    try:
+        assert mod.register() == "xroute_env/ordering-training-v0"
+        assert reg == {"xroute_env/ordering-training-v0": "xroute_env_b200.gym_env:OrderingTrainingEnv"}
+        for name in ("reset", "step", "close"):
+            assert callable(getattr(mod.OrderingTrainingEnv, name)) and callable(getattr(mod.OrderingTrainingVecEnv, name))
+    finally:
+        monkeypatch.undo()
+        importlib.reload(gym_env)
