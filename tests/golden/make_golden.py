@@ -12,6 +12,8 @@ fixtures hold inputs (seeded node lists) and the outputs the reference computes.
                        of the shipped PPO log
                        (baseline/PPO/results/2023-04-27--05-00-38/events.out.tfevents.*),
                        the known-answer vectors of train_PPO.py:101-102.
+  mcts_dispatch.npz    the messages of the reference's own MCTS dispatcher (trainer4/dispatcher.py)
+                       driven with a fake mixer: prefix-re-route bookkeeping, delta metrics, is_routed.
   game_episode.npz     a 2-net episode driven through the UNMODIFIED reference Game
                        (baseline/baseline_utils.py:383-481) against a fake REQ-side
                        simulator: pins the cumulative->delta differencing, done flag,
@@ -299,8 +301,107 @@ def make_a3c_features():
     print("a3c_features.npz:", len(cases), "cases; cost", out["cost_out"].tolist())
 
 
+def make_mcts_dispatch():
+    """mcts_dispatch.npz: the messages the reference's own Dispatcher.run (baseline/xroute/trainer4/dispatcher.py:36-122,
+    unmodified) hands its algorithm when its mixer -- the OpenROAD process that routes a complete net order -- is replaced
+    by a fake one backed by this repo's CPU oracle: pins the prefix-re-route bookkeeping (order = chosen + remaining,
+    cumulative -> delta metrics with the default order's cost in the first message, is_routed in node property 3,
+    remaining-net lists, is_done)."""
+    import threading
+    import types
+    import zmq
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200.instances import ispd18_geometry, make_instance
+    from xroute_env_b200.mcts import graph_features
+    os.environ.setdefault("PROTOCOL_BUFFERS_PYTHON_IMPLEMENTATION", "python")
+    sys.path.insert(0, os.path.join(REF, "baseline", "xroute"))
+    import net_ordering_pb2 as pb
+    proto_pkg = types.ModuleType("proto"); proto_pkg.net_ordering_pb2 = pb
+    sys.modules["proto"] = proto_pkg; sys.modules["proto.net_ordering_pb2"] = pb
+    geom = ispd18_geometry(30, 28, 6)
+    inst = make_instance(geom, 7, 4711, p_obstacle=0.15)
+    nodes, _ = graph_features(geom, inst)
+    env = OracleEnv(geom, inst)
+
+    class FakeMixer:
+        """get_observation / set_net_list / get_result / ack of trainer4/mixer.py:52-69 on the oracle"""
+        pending = None
+
+        def __init__(self, **kw):
+            pass
+
+        def start(self):
+            pass
+
+        def _request(self, cum):
+            r = pb.Request()
+            r.dim_x, r.dim_y, r.dim_z = geom.X, geom.Y, geom.Z
+            r.reward_violation, r.reward_wire_length, r.reward_via = cum
+            r.nets[:] = [n - 1 for n in inst.net_ids]
+            for row in nodes:
+                r.graph.node_properties.add().values[:] = [float(v) for v in row]
+            return r
+
+        def get_observation(self):
+            if FakeMixer.pending is not None:
+                r, FakeMixer.pending = FakeMixer.pending, None
+                return r
+            return self._request((0, 0, 0))
+
+        get_result = get_observation
+
+        def set_net_list(self, net_list):
+            env.reset()
+            m = None
+            for k in net_list:
+                m = env.step(int(k) + 1)
+            FakeMixer.pending = self._request((m["violation"], m["wirelength"], m["via"]))
+
+        def ack(self):
+            pass
+
+    mixer_mod = types.ModuleType("mixer"); mixer_mod.Mixer = FakeMixer
+    sys.modules["mixer"] = mixer_mod
+    sys.path.insert(0, os.path.join(REF, "baseline", "xroute", "trainer4"))
+    import dispatcher as ref_dispatcher
+    port = 17651
+    choices = [4, 0, 6, 2, 5, 1, 3]                        # 0-based net indices, in the order the "agent" picks them
+    log = []
+
+    def algorithm():
+        ctx = zmq.Context()
+        sock = ctx.socket(zmq.REP)
+        sock.bind(f"tcp://127.0.0.1:{port}")
+        k = 0
+        while True:
+            msg = pb.Message(); msg.ParseFromString(sock.recv())
+            q = msg.request
+            log.append((list(q.nets), [q.reward_violation, q.reward_wire_length, q.reward_via],
+                        [int(p.values[3]) for p in q.graph.node_properties], bool(q.is_done)))
+            if q.is_done:
+                sock.send(b"\0")
+                break
+            out = pb.Message(); out.response.net_index = choices[k]; k += 1
+            sock.send(out.SerializeToString())
+        sock.close(0); ctx.term()
+
+    th = threading.Thread(target=algorithm)
+    th.start()
+    d = ref_dispatcher.Dispatcher(openroad_executable="none", port_to_alg=port, port_from_or_mixer=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        d.run()
+    th.join(timeout=30)
+    assert len(log) == len(choices) + 1 and log[-1][3]
+    np.savez_compressed(
+        os.path.join(HERE, "mcts_dispatch.npz"), dims=np.array([geom.X, geom.Y, geom.Z]), seed=np.array([4711]),
+        block_xyz=inst.block_xyz, ap_net=inst.ap_net, ap_pin=inst.ap_pin, ap_xyz=inst.ap_xyz, choices=np.array(choices),
+        nets=np.array([l[0] + [-1] * (7 - len(l[0])) for l in log]), delta=np.array([l[1] for l in log]),
+        is_routed=np.array([l[2] for l in log]), is_done=np.array([l[3] for l in log]))
+    print("mcts_dispatch.npz:", len(log), "messages; first delta (cost of the default order)", log[0][1])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["obs", "reward", "game", "a3c"]
+    which = sys.argv[1:] or ["obs", "reward", "game", "a3c", "mcts"]
     if "obs" in which:
         make_obs_cases()
     if "reward" in which:
@@ -309,3 +410,5 @@ if __name__ == "__main__":
         make_game_episode()
     if "a3c" in which:
         make_a3c_features()
+    if "mcts" in which:
+        make_mcts_dispatch()
