@@ -191,7 +191,7 @@ def _pool_cores(bytes_per_worker: float) -> int:
 def cpu_run(cores: int, budget_s: float, preset: str = PRESET, n_nets: int = N_NETS, region: str | None = None):
     """Oracle port on `cores` processes for about `budget_s` seconds.  Returns (env-steps/s, steps, cells settled/s, wall)."""
     fn = _cpu_region_worker if region else _cpu_worker
-    mk = (lambda i: (region, 64 * i, 64, budget_s)) if region else (lambda i: (preset, n_nets, 8 * i, 8, budget_s))
+    mk = (lambda i: (region, 64 * i, 64, budget_s)) if region else (lambda i: (preset, n_nets, 64 * i, 64, budget_s))
     if cores == 1:
         res = [fn(mk(0))]
     else:
