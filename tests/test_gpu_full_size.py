@@ -109,3 +109,45 @@ def test_config4_syn1024_congested_nets_on_and_off_chip(engine):
     else:
         assert rc["frontier_nets"] == 12 and rc["global_nets"] == 0, rc
     vg.close()
+
+
+def test_config4_syn1024_16_envs_full_episode_both_engines():
+    """configs[3] at half a GPU's shard: 16 environments x 128 clustered nets on the 1024x1024x9 grid, the WHOLE episode,
+    routed by the frontier engine and by the sweep engines (16-CTA windows + full-grid sweeps): cumulative metrics of every
+    environment at every step and a hash of every final occupancy must agree; environment 0 is also checked bit-exactly
+    (paths, costs, metrics) against the CPU oracle for the first 24 steps."""
+    from oracle.oracle import OracleEnv
+    from xroute_env_b200 import VecGame
+    geom = preset_geometry("SYN-1024")
+    n_envs, n_nets = 16, 128
+    insts = make_batch(geom, n_envs, n_nets, 4040, hot_spots=16, hot_sigma=32.0)
+    rng = np.random.default_rng(4)
+    orders = np.stack([rng.permutation(i.net_ids) for i in insts], 1).astype(np.int32)
+    w = (np.arange(geom.cells, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(12345)) | np.uint64(1)
+    out = {}
+    for engine in (0, 1):
+        vg = VecGame(geom, insts, device=0, obs_max_nets=8, engine=engine)
+        vg.reset()
+        orc = OracleEnv(geom, insts[0]) if engine == 0 else None
+        cums = []
+        for t in range(n_nets):
+            vg.step(orders[t])
+            _, _, cum = vg.results_host_np()
+            cums.append(cum.copy())
+            if orc is not None and t < 24:
+                m = orc.step(int(orders[t, 0]))
+                assert [int(v) for v in cum[0]] == [m["violation"], m["wirelength"], m["via"], m["blocked"], m["shorted"], m["overflow"]], t
+                oc, oo, ocost = orc.last_paths(); gc, go, gcost = vg.paths(0)
+                assert np.array_equal(oc, gc) and np.array_equal(ocost, gcost), t
+        assert bool(vg.done.all())
+        hashes = []
+        for e in range(n_envs):
+            usage, owner = vg.state(e)
+            hashes.append(int((usage.reshape(-1).astype(np.uint64) * w).sum() ^ (owner.reshape(-1).astype(np.uint64) * (w >> np.uint64(7))).sum()))
+        out[engine] = (np.stack(cums), hashes, vg.route_counters())
+        vg.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1]
+    rc = out[0][2]                                           # hybrid: the wide few-pin nets of this small batch take the sweep kernels
+    assert rc["frontier_nets"] + rc["window_nets"] + rc["global_nets"] == n_envs * n_nets and rc["frontier_nets"] > 0
+    assert out[1][2]["frontier_nets"] == 0
