@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
         const uint32_t Bfin = (uint32_t)(best >> 32);
         if (best == ~0ull || Bfin >= XR_INF) { if (tid == 0) S->err = 1; __syncthreads(); break; }
         // ---- canonical backtrace by warp 0: predecessor order [last, +x, -x, +y, -y, +z, -z].  One round trip probes all
-        // six directions five cells deep (lane = 5 dir + k checks the step from c - k delta to c - (k+1) delta); a run
-        // that is still going after five cells continues 32 cells per round trip along its direction.  The walk reads
+        // six directions several cells deep (a lane checks the step from c - k delta to c - (k+1) delta); a run that is
+        // still going at full depth continues 32 cells per round trip along its direction.  The walk reads
         // the field of this connection only; its cells join the tree afterwards.
         const int pn0 = pn;
         if (warp == 0) {
@@ -567,8 +567,15 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
             };
             while (dc != 0) {
                 __syncwarp();
-                // all six directions, five steps deep
-                const int dir = lane / 5, k = lane - 5 * dir;
+                // one round trip probes all six directions: the two preferred directions of the cell's layer 11 steps deep
+                // (lanes 0-10, 11-21), the other four 2 steps deep (lanes 22-29) -- runs are long along the preferred
+                // direction and short across it
+                const int p0 = s_pref[cz] == 0 ? 0 : 2;
+                auto base_of = [&](int dd) { return dd == p0 ? 0 : dd == p0 + 1 ? 11 : 22 + 2 * (dd >= 4 ? dd - 2 : (dd & 1)); };
+                auto depth_of = [&](int dd) { return (dd == p0 || dd == p0 + 1) ? 11 : 2; };
+                int dir, k;
+                if (lane < 22) { dir = p0 + (lane >= 11 ? 1 : 0); k = lane - (lane >= 11 ? 11 : 0); }
+                else { const int o = (lane - 22) >> 1; dir = o < 2 ? (p0 == 0 ? 2 + o : o) : 2 + o; k = (lane - 22) & 1; }
                 int ddx = 0, ddy = 0, ddz = 0;
                 bool ok = false;
                 uint32_t db = XR_INF;
@@ -578,22 +585,23 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 }
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                 int pick = -1;
-                if (last >= 0 && ((m >> (5 * last)) & 1u)) pick = last;
+                if (last >= 0 && ((m >> base_of(last)) & 1u)) pick = last;
                 else {
 #pragma unroll
-                    for (int dd = 5; dd >= 0; dd--) if ((m >> (5 * dd)) & 1u) pick = dd;
+                    for (int dd = 5; dd >= 0; dd--) if ((m >> base_of(dd)) & 1u) pick = dd;
                 }
                 if (pick < 0) { fail = 3; break; }
-                const unsigned bits = (m >> (5 * pick)) & 31u;
-                const int run = bits == 31u ? 5 : (__ffs(~bits) - 1);
+                const int pbase = base_of(pick), pdepth = depth_of(pick);
+                const unsigned bits = (m >> pbase) & ((1u << pdepth) - 1u);
+                const int run = bits == ((1u << pdepth) - 1u) ? pdepth : (__ffs(~bits) - 1);
                 if (dir == pick && k < run && lane < 30) record(cx - k * ddx, cy - k * ddy, cz - k * ddz, dir, q + k);
                 q += run;
-                dc = __shfl_sync(0xFFFFFFFFu, db, 5 * pick + run - 1);
+                dc = __shfl_sync(0xFFFFFFFFu, db, pbase + run - 1);
                 int pdx, pdy, pdz; dir_delta(pick, pdx, pdy, pdz);
                 cx -= run * pdx; cy -= run * pdy; cz -= run * pdz;
                 last = pick;
                 // a straight run that is still going: 32 cells per round trip
-                while (dc != 0 && run == 5) {
+                while (dc != 0 && run == pdepth) {
                     __syncwarp();
                     bool ok2 = false;
                     const uint32_t db2 = step_ok(cx - lane * pdx, cy - lane * pdy, cz - lane * pdz, last, ok2);
