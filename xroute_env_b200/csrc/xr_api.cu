@@ -70,7 +70,7 @@ struct XrEnv {
     int engine = 0;                     // 0 = frontier, 1 = window kernels + full-grid sweeps (round-1 engines)
     FrParams fr_big = {}, fr_small = {};// list capacities for "one CTA per SM" and "several CTAs per SM" launches
     int fr_threads_big = FR_T, fr_threads_small = 512;
-    int hybrid_area = 4000, hybrid_pins = 3;   // hybrid: nets of at most hybrid_pins pins whose access-point box covers at least hybrid_area cells take the sweep kernels (0 = never)
+    int hybrid_area = 4000, hybrid_pins = 5;   // hybrid: nets of at most hybrid_pins pins whose access-point box covers at least hybrid_area cells take the sweep kernels (0 = never)
     std::vector<int32_t> h_area;        // [N][max_nets+1] cells of the net's access-point bounding box (x by y)
     int guide_cap = 0;                  // guide boxes per environment the device table holds (grown on demand)
     int metrics_mode = 0;               // 0 = congestion counts maintained by the commits, 1 = full scan (k_metrics) every step
@@ -832,8 +832,18 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
                 // one CTA per net, a step is as long as its largest search, and the largest searches are the few-pin
                 // nets with a wide bounding box (the search floods the box on ~3 layers: the sweep kernels do that
                 // faster on a cluster of CTAs).  Same results either way.
-                const bool wide = hybrid && np <= env->hybrid_pins && WX > 0 && WX < 1024 && WY < 1024 &&
-                                  env->h_area[(size_t)i * (g.max_nets + 1) + a] >= env->hybrid_area;
+                bool wide = hybrid && np <= env->hybrid_pins && WX > 0 && WX < 1024 && WY < 1024 &&
+                            env->h_area[(size_t)i * (g.max_nets + 1) + a] >= env->hybrid_area &&
+                            env->h_naps[(size_t)i * (g.max_nets + 1) + a] <= WIN_TGT_CAP;
+                if (wide && np > 3) {                     // nets of 4+ pins only onto a cluster: when their window fits none they
+                    bool fits = false;                    // would take the full-grid sweeps in HBM, which only pays for 2-3 pins
+                    for (int b = 0; b < NB_BAND && !fits; b++) {
+                        if (CS[b] < mc) continue;
+                        const int H = (WY + CS[b] - 1) / CS[b];
+                        fits = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX)) <= env->smem_cap;
+                    }
+                    wide = fits;
+                }
                 if (!wide) {
                     fr_order.push_back(((long long)(65535 - std::min(np, 65535)) << 32) | (unsigned)i);   // many-pin nets first
                     env->n_frontier_nets++;
