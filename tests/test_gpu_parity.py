@@ -73,11 +73,13 @@ def test_route_paths_agree_across_engines(kw):
 
 @pytest.mark.parametrize("knobs", [{}, {"XR_FR_RAY": "1"}, {"XR_FR_RAY": "3", "XR_FR_DELTA": "0"}, {"XR_FR_DELTA": "400"},
                                    {"XR_FR_DELTA": "1000000"}, {"XR_FR_CAP": "64"}, {"XR_FR_THREADS": "64", "XR_FR_CAP": "128"},
-                                   {"XR_FR_THREADS": "128", "XR_FR_RAY": "5"}],
-                         ids=["default", "ray1", "ray3-delta0", "delta400", "delta-inf", "spill", "t64-spill", "t128-ray5"])
+                                   {"XR_FR_THREADS": "128", "XR_FR_RAY": "5"}, {"XR_FR_PARK": "1", "XR_FR_BAND": "1"},
+                                   {"XR_FR_PARK": "16", "XR_FR_DELTA": "100", "XR_FR_DMAX": "1", "XR_FR_CAP": "64"}, {"XR_FR_PARK": "0"}],
+                         ids=["default", "ray1", "ray3-delta0", "delta400", "delta-inf", "spill", "t64-spill", "t128-ray5",
+                              "park1", "park16-spill", "nopark"])
 def test_frontier_engine_knobs(knobs, monkeypatch):
     """The default engine (goal-directed frontier search, csrc/xr_frontier.cu) for every ray length, bucket width,
-    block size and with open lists that spill to global memory: the knobs change the schedule of the relaxations,
+    block size, with open lists that spill to global memory and with far-list parking from the first entry on: the knobs change the schedule of the relaxations,
     never a distance the target choice or the walk reads -- paths, costs, metrics and observations stay bit-exact.
     metrics_mode 1 on top checks the commit-maintained congestion counts against the full scan."""
     for k, v in knobs.items():

@@ -30,9 +30,9 @@ for t in range(n_steps):
     pins = len(set(insts[k].ap_pin[insts[k].ap_net == acts[k]].tolist()))
     worst.append((int(r[k, 0]), t, k, pins, r[k].tolist()))
 torch.cuda.synchronize()
-print("slowest net of every step: cycles | step env pins | rounds expanded conns expand_cyc classify_cyc n_ap max_open")
+print("slowest net of every step: cycles | step env pins | rounds expanded conns expand_cyc classify_cyc refill_cyc refills max_open")
 for w in sorted(worst, reverse=True)[:12]:
-    print(f"   {w[0]:9d} | {w[1]:2d} {w[2]:2d} {w[3]:2d} | {w[4][1]:4d} {w[4][2]:7d} {w[4][3]:3d} {w[4][4]:9d} {w[4][5]:9d} {w[4][6]:3d} {w[4][7]:6d}")
+    print(f"   {w[0]:9d} | {w[1]:2d} {w[2]:2d} {w[3]:2d} | {w[4][1]:4d} {w[4][2]:7d} {w[4][3]:3d} {w[4][4]:9d} {w[4][5]:9d} {w[4][6] & ((1 << 40) - 1):9d} {w[4][6] >> 40:4d} {w[4][7]:6d}")
 A = np.array(allrec, np.float64)
 print("by pin count: nets | mean cycles | max cycles | rounds | expanded | conns | expand cyc | classify cyc | cycles/round | cycles/expanded")
 for lo, hi in ((2, 3), (4, 7), (8, 12), (13, 99)):

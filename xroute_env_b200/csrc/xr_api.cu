@@ -297,6 +297,13 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         if (const char *e = getenv("XR_FR_DELTA")) env->fr_big.delta = env->fr_small.delta = (uint32_t)std::max(0, atoi(e));
         env->fr_big.dmax = env->fr_small.dmax = 4;
         if (const char *e = getenv("XR_FR_DMAX")) env->fr_big.dmax = env->fr_small.dmax = std::max(1, atoi(e));
+        // the wide variant of the kernel (far list from 4096 open entries on, band = one full-width bucket) for grids of more
+        // than 2 M cells: their wide nets hold 10^5 open entries; smaller grids keep the shorter round of the plain variant
+        int park = cp > (2 << 20) ? 4096 : 0, band = 1;
+        if (const char *e = getenv("XR_FR_PARK")) park = std::max(0, atoi(e));
+        if (const char *e = getenv("XR_FR_BAND")) band = std::max(1, atoi(e));
+        env->fr_big.park_min = env->fr_small.park_min = park;
+        env->fr_big.band = env->fr_small.band = (uint32_t)band * std::max(env->fr_big.delta, 1u) * (uint32_t)env->fr_big.dmax;
         if (const char *e = getenv("XR_FR_RAY")) env->fr_big.ray = env->fr_small.ray = std::min(FR_RAY, std::max(1, atoi(e)));
         if (const char *e = getenv("XR_FR_THREADS")) env->fr_threads_big = env->fr_threads_small = std::min(FR_T, std::max(64, atoi(e) / 32 * 32));
         if (const char *e = getenv("XR_FR_CAP")) { env->fr_big.cap_s = env->fr_small.cap_s = std::max(64, atoi(e)); env->fr_big.cap_e = env->fr_small.cap_e = std::max(64, atoi(e) / 2); }

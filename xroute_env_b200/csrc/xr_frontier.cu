@@ -44,6 +44,8 @@ struct FrSm {
     unsigned long long best;
     int rx0, rx1, ry0, ry1;  // tiles holding the net's access points
     int dmul;              // current bucket width in units of delta
+    int far_n[2];          // entries parked in the two far lists (global memory only)
+    uint32_t far_min[2];   // smallest f parked in each
 };
 
 __device__ __forceinline__ int fr_agg_inc(int *ctr) {
@@ -61,6 +63,9 @@ __device__ __forceinline__ int fr_agg_inc(int *ctr) {
 #define FR_TILE_SHIFT 4    // heuristic tiles of 16 x 16 cells
 #define FR_MAXTILES 4096
 
+// WIDE: the variant for grids whose searches hold 10^5 open entries (far-list parking, task prefetch, batched
+// classification loads); the plain variant has the shorter round for the small searches of small grids.
+template <bool WIDE>
 __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, const int *__restrict__ env_list, FrParams P) {
     const int env = env_list[blockIdx.x];
     const int net = d.act[2 * env + 1];
@@ -91,13 +96,17 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
     uint8_t *s_apconn = reinterpret_cast<uint8_t *>(sp); sp += FR_MAXAP / 4;
     uint8_t *s_apon = reinterpret_cast<uint8_t *>(sp); sp += FR_MAXAP / 4;
     // ---- global spill of the lists
-    uint32_t *spill = d.fr_spill + (size_t)env * (4 * (size_t)P.cap_g + 4 * (size_t)P.cap_ge);
-    uint32_t *ge_pc = spill + 4 * (size_t)P.cap_g, *ge_d = ge_pc + P.cap_ge;         // single-step tasks
+    uint32_t *spill = d.fr_spill + (size_t)env * (8 * (size_t)P.cap_g + 4 * (size_t)P.cap_ge);
+    uint32_t *farl = spill + 4 * (size_t)P.cap_g;                                     // the two far lists
+    uint32_t *ge_pc = farl + 4 * (size_t)P.cap_g, *ge_d = ge_pc + P.cap_ge;          // single-step tasks
     uint32_t *gr_pc = ge_d + P.cap_ge, *gr_d = gr_pc + P.cap_ge;                      // ray tasks
     const int cap_l = P.cap_s + P.cap_g, cap_x = P.cap_e + P.cap_ge;
     auto put_l = [&](int w, int i, uint32_t pc, uint32_t f) {
         if (i < P.cap_s) { uint32_t *q = l_base + 2 * (size_t)w * P.cap_s + i; q[0] = pc; q[P.cap_s] = f; }
         else { uint32_t *q = spill + 2 * (size_t)w * P.cap_g + (i - P.cap_s); __stcg(q, pc); __stcg(q + P.cap_g, f); }
+    };
+    auto put_f = [&](int w, int i, uint32_t pc, uint32_t f) {
+        uint32_t *q = farl + 2 * (size_t)w * P.cap_g + i; __stcg(q, pc); __stcg(q + P.cap_g, f);
     };
     auto put_e = [&](int i, uint32_t pc, uint32_t dv) {
         if (i < P.cap_e) { e_pc[i] = pc; e_d[i] = dv; }
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
     const int rw = rtx1 - rtx0 + 1, n_reg = min(rw * (rty1 - rty0 + 1), FR_MAXTILES);
     const bool uni_x = g.uniform_x != 0, uni_y = g.uniform_y != 0;
 #ifdef FR_TIMING
-    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, n_expanded = 0, max_open = 0;   // seed+connect, boxes+push, classify, expand, target, walk, commit
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, n_expanded = 0, max_open = 0, n_refill = 0;   // seed+connect, boxes+push, classify, expand, target, walk, commit
     const long long tstart = clock64();
     long long tlast = tstart;
 #endif
@@ -230,6 +239,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
         if (tid == 0) {
             S->cnt[0] = 0; S->cnt[1] = 0; S->fmin[0] = 0xFFFFFFFFu; S->fmin[1] = 0xFFFFFFFFu;
             S->nexp[0] = 0; S->nexp[1] = 0; S->nray[0] = 0; S->nray[1] = 0; S->B = XR_INF; S->nbox = 0; S->best = ~0ull; S->dmul = 1;
+            S->far_n[0] = 0; S->far_n[1] = 0; S->far_min[0] = 0xFFFFFFFFu; S->far_min[1] = 0xFFFFFFFFu;
         }
         // ---- the tree so far becomes the source set of this epoch (distance 0; the flag bits of a word stay)
         if (first) {
@@ -331,31 +341,89 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
         }
         FR_TICK(1);
         // ---- rounds
-        int cur = 0, par = 0;
+        // Parking: a wide search leaves behind, for every cell it expands, the entries of the steps that lead away from
+        // the targets.  Their f lies above the bucket for a long time (most are dropped unexpanded when the target is
+        // reached), and an open list that is classified front to back every round pays for them every round.  Once
+        // the open list holds more than park_min entries, entries with f > far_thr go to a far list in global memory,
+        // which is only read again when the open list has nothing below its smallest f (then far_thr moves up by
+        // `band` and the entries below it come back).  The order of expansion does not change the result: the search
+        // ends when no open entry -- parked ones included -- has f <= B.
+        int cur = 0, par = 0, fc = 0;
+        uint32_t far_thr = 0xFFFFFFFFu;
         for (;;) {
             __syncthreads();                              // (A) the lists, counters and B of the previous round are published
             FR_TICK(3);
             const int n = min(S->cnt[cur], cap_l);
             const uint32_t fm = S->fmin[cur], Bv = S->B;
+            int fn = 0;
+            uint32_t fmn = 0xFFFFFFFFu;
+            if (WIDE && far_thr != 0xFFFFFFFFu) {         // (the classification below appends to the far list: everyone reads first)
+                fn = min(S->far_n[fc], P.cap_g); fmn = S->far_min[fc];
+                __syncthreads();
+            }
+            if (WIDE && fn > 0 && fmn <= Bv && (n == 0 || fm >= fmn)) {
+                // ---- the far list comes back: entries up to the new far_thr join the open list, the rest is compacted into
+                // the other far list (stale entries and entries above B are dropped on the way)
+                const uint32_t nthr = min(fm, fmn) + P.band;
+                const int fo = fc ^ 1;
+                uint32_t fl_n = 0xFFFFFFFFu, fl_f = 0xFFFFFFFFu;
+                const uint32_t *fq = farl + 2 * (size_t)fc * P.cap_g;
+                for (int i0 = 0; i0 < fn; i0 += 4 * T) {
+                    uint32_t pc[4], f[4];
+                    unsigned long long wv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int i = i0 + k * T + tid;
+                        f[k] = 0xFFFFFFFFu; pc[k] = 0;
+                        if (i < fn) { pc[k] = __ldcg(fq + i); f[k] = __ldcg(fq + P.cap_g + i); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        wv[k] = 0ull;
+                        if (f[k] <= Bv) wv[k] = __ldcg(dist + ((size_t)((pc[k] >> 20) & 15) * Y + ((pc[k] >> 10) & 1023)) * Xp + (pc[k] & 1023));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (f[k] > Bv) continue;
+                        if (dval(wv[k]) < f[k] - hval(pc[k] & 1023, (pc[k] >> 10) & 1023)) continue;
+                        if (f[k] <= nthr) {
+                            const int idx = fr_agg_inc(&S->cnt[cur]);
+                            if (idx < cap_l) put_l(cur, idx, pc[k], f[k]); else S->err = 5;
+                            fl_n = min(fl_n, f[k]);
+                        } else {
+                            const int idx = fr_agg_inc(&S->far_n[fo]);
+                            if (idx < P.cap_g) put_f(fo, idx, pc[k], f[k]); else S->err = 5;
+                            fl_f = min(fl_f, f[k]);
+                        }
+                    }
+                }
+                fl_n = __reduce_min_sync(0xFFFFFFFFu, fl_n); fl_f = __reduce_min_sync(0xFFFFFFFFu, fl_f);
+                if (lane == 0 && fl_n != 0xFFFFFFFFu) atomicMin(&S->fmin[cur], fl_n);
+                if (lane == 0 && fl_f != 0xFFFFFFFFu) atomicMin(&S->far_min[fo], fl_f);
+                __syncthreads();
+                if (tid == 0) { S->far_n[fc] = 0; S->far_min[fc] = 0xFFFFFFFFu; }
+                fc = fo; far_thr = nthr;
+                if (S->err) break;
+#ifdef FR_TIMING
+                { const long long t__ = clock64(); ph[7] += t__ - tlast; tlast = t__; n_refill++; }
+#endif
+                continue;
+            }
             if (n == 0 || fm > Bv) break;
             n_rounds++;
             const uint32_t thr = fm + P.delta * (uint32_t)S->dmul;
+            if (WIDE && far_thr == 0xFFFFFFFFu && P.park_min > 0 && n > P.park_min) far_thr = fm + P.band;
             // list pressure (a quarter of the capacity in use): drop the stale entries of a cell here and push a cell only
             // when its word really went down, so that the list holds at most one live entry per cell and lowering
-            const bool tight = n > cap_l / 4;
+            const bool tight = n + fn > cap_l / 4;
             const int nxt = cur ^ 1;
-            uint32_t fl = 0xFFFFFFFFu;
+            uint32_t fl = 0xFFFFFFFFu, flf = 0xFFFFFFFFu;
             // classify: expand now (one single-step task + a ray task per ray bit) / keep for later / drop (f > B)
-            for (int i0 = 0; i0 < n; i0 += T) {
-                const int i = i0 + tid;
-                if (i >= n) break;
-                uint32_t pc, f;
-                if (i < P.cap_s) { const uint32_t *q = l_base + 2 * (size_t)cur * P.cap_s + i; pc = q[0]; f = q[P.cap_s]; }
-                else { const uint32_t *q = spill + 2 * (size_t)cur * P.cap_g + (i - P.cap_s); pc = __ldcg(q); f = __ldcg(q + P.cap_g); }
-                if (f > Bv) continue;
+            auto classify = [&](const uint32_t pc, const uint32_t f) {
+                if (f > Bv) return;
                 if (tight) {
                     const int ex = pc & 1023, ey = (pc >> 10) & 1023, ez = (pc >> 20) & 15;
-                    if (dval(__ldcg(dist + ((size_t)ez * Y + ey) * Xp + ex)) < f - hval(ex, ey)) continue;
+                    if (dval(__ldcg(dist + ((size_t)ez * Y + ey) * Xp + ex)) < f - hval(ex, ey)) return;
                 }
                 if (f <= thr) {
                     const uint32_t d0 = f - hval(pc & 1023, (pc >> 10) & 1023);
@@ -367,10 +435,37 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                         if (pc & FR_RAY_POS) { if (q < cap_x) put_r(q, pc & 0x00FFFFFFu, d0); else S->err = 5; q++; }
                         if (pc & FR_RAY_NEG) { if (q < cap_x) put_r(q, (pc & 0x00FFFFFFu) | FR_RAY_NEG, d0); else S->err = 5; }
                     }
-                } else {
+                } else if (!WIDE || f <= far_thr) {
                     const int idx = fr_agg_inc(&S->cnt[nxt]);
                     if (idx < cap_l) put_l(nxt, idx, pc, f); else S->err = 5;
                     fl = min(fl, f);
+                } else {
+                    const int idx = fr_agg_inc(&S->far_n[fc]);
+                    if (idx < P.cap_g) put_f(fc, idx, pc, f); else S->err = 5;
+                    flf = min(flf, f);
+                }
+            };
+            if constexpr (WIDE) {
+                for (int i0 = 0; i0 < n; i0 += 4 * T) {     // four entries per thread in flight: the spilled part is an L2 round trip each
+                    uint32_t pc4[4], f4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int i = i0 + k * T + tid;
+                        pc4[k] = 0; f4[k] = 0xFFFFFFFFu;
+                        if (i < n) {
+                            if (i < P.cap_s) { const uint32_t *q = l_base + 2 * (size_t)cur * P.cap_s + i; pc4[k] = q[0]; f4[k] = q[P.cap_s]; }
+                            else { const uint32_t *q = spill + 2 * (size_t)cur * P.cap_g + (i - P.cap_s); pc4[k] = __ldcg(q); f4[k] = __ldcg(q + P.cap_g); }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) classify(pc4[k], f4[k]);
+                }
+            } else {
+                for (int i = tid; i < n; i += T) {
+                    uint32_t pc, f;
+                    if (i < P.cap_s) { const uint32_t *q = l_base + 2 * (size_t)cur * P.cap_s + i; pc = q[0]; f = q[P.cap_s]; }
+                    else { const uint32_t *q = spill + 2 * (size_t)cur * P.cap_g + (i - P.cap_s); pc = __ldcg(q); f = __ldcg(q + P.cap_g); }
+                    classify(pc, f);
                 }
             }
             __syncthreads();                              // (B)
@@ -392,15 +487,24 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
             };
             // Push a lowered cell (warp-aggregated append to the next list).  Called by all 32 lanes.
             auto push = [&](bool keep, uint32_t pcv, uint32_t fv) {
-                const unsigned mk = __ballot_sync(0xFFFFFFFFu, keep);
-                if (mk == 0u) return;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&S->cnt[nxt], __popc(mk));
+                const bool park = WIDE && keep && fv > far_thr;
+                keep = keep && !park;
+                const unsigned mk = __ballot_sync(0xFFFFFFFFu, keep), mp = WIDE ? __ballot_sync(0xFFFFFFFFu, park) : 0u;
+                if ((mk | mp) == 0u) return;
+                int base = 0, basep = 0;
+                if (lane == 0 && mk) base = atomicAdd(&S->cnt[nxt], __popc(mk));
+                if (WIDE && lane == 0 && mp) basep = atomicAdd(&S->far_n[fc], __popc(mp));
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (WIDE) basep = __shfl_sync(0xFFFFFFFFu, basep, 0);
                 if (keep) {
                     const int q = base + __popc(mk & ((1u << lane) - 1u));
                     if (q < cap_l) put_l(nxt, q, pcv, fv); else S->err = 5;
                     fl = min(fl, fv);
+                }
+                if (park) {
+                    const int q = basep + __popc(mp & ((1u << lane) - 1u));
+                    if (q < P.cap_g) put_f(fc, q, pcv, fv); else S->err = 5;
+                    flf = min(flf, fv);
                 }
             };
             // ---- ray tasks, one LANE per cell: 8 lanes relax up to `ray` cells along the layer's preferred direction.
@@ -409,15 +513,35 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
             // shoots on (same direction); the others were relaxed onwards by this very ray, and backwards lies the
             // smaller distance they came from.
             // Ray lanes first, single-step lanes behind them (from a warp boundary on), dealt to the warps round robin.
-            const int R32 = (FR_RAY * nR + 31) & ~31;
-            for (int w0 = warp * 32; w0 < R32 + 4 * nE; w0 += T) {
+            // A lane's task of the next trip is fetched before the current one is worked on: tasks beyond cap_e live in
+            // global memory, and the fetch would otherwise sit in front of the cell loads on the critical path.
+            const int R32 = (FR_RAY * nR + 31) & ~31, n_lanes = R32 + 4 * nE;
+            auto fetch = [&](int w0, uint32_t &pc, uint32_t &d0) {
+                if (w0 >= n_lanes) return;
+                if (w0 < R32) {
+                    const int w = w0 + lane, t = w < FR_RAY * nR ? w / FR_RAY : 0;
+                    if (t < P.cap_e) { pc = r_pc[t]; d0 = r_d[t]; }
+                    else { pc = __ldcg(gr_pc + (t - P.cap_e)); d0 = __ldcg(gr_d + (t - P.cap_e)); }
+                } else {
+                    const int w = w0 - R32 + lane, t = w < 4 * nE ? w >> 2 : 0;
+                    if (t < P.cap_e) { pc = e_pc[t]; d0 = e_d[t]; }
+                    else { pc = __ldcg(ge_pc + (t - P.cap_e)); d0 = __ldcg(ge_d + (t - P.cap_e)); }
+                }
+            };
+            uint32_t pc_n = 0, d0_n = 0;
+            if (WIDE) fetch(warp * 32, pc_n, d0_n);
+            for (int w0 = warp * 32; w0 < n_lanes; w0 += T) {
+              uint32_t pc = pc_n, d0 = d0_n;
+              if (WIDE) fetch(w0 + T, pc_n, d0_n);
               if (w0 < R32) {
                 const int w = w0 + lane;
                 const bool act = w < FR_RAY * nR;
-                const int t = act ? w / FR_RAY : 0, k = w & (FR_RAY - 1);
-                uint32_t pc, d0;
-                if (t < P.cap_e) { pc = r_pc[t]; d0 = r_d[t]; }
-                else { pc = __ldcg(gr_pc + (t - P.cap_e)); d0 = __ldcg(gr_d + (t - P.cap_e)); }
+                const int k = w & (FR_RAY - 1);
+                if constexpr (!WIDE) {
+                    const int t = act ? w / FR_RAY : 0;
+                    if (t < P.cap_e) { pc = r_pc[t]; d0 = r_d[t]; }
+                    else { pc = __ldcg(gr_pc + (t - P.cap_e)); d0 = __ldcg(gr_d + (t - P.cap_e)); }
+                }
                 const int x = pc & 1023, y = (pc >> 10) & 1023, z = (pc >> 20) & 15;
                 const int sgn = (pc & FR_RAY_NEG) ? -1 : 1;
                 const size_t cp0 = ((size_t)z * Y + y) * Xp + x;
@@ -465,10 +589,12 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 // ---- single-step tasks, one lane per cell: the two wrong-way neighbours and the two vias of every expanded cell
                 const int w = w0 - R32 + lane;
                 const bool act = w < 4 * nE;
-                const int t = act ? w >> 2 : 0, j = w & 3;
-                uint32_t pc, d0;
-                if (t < P.cap_e) { pc = e_pc[t]; d0 = e_d[t]; }
-                else { pc = __ldcg(ge_pc + (t - P.cap_e)); d0 = __ldcg(ge_d + (t - P.cap_e)); }
+                const int j = w & 3;
+                if constexpr (!WIDE) {
+                    const int t = act ? w >> 2 : 0;
+                    if (t < P.cap_e) { pc = e_pc[t]; d0 = e_d[t]; }
+                    else { pc = __ldcg(ge_pc + (t - P.cap_e)); d0 = __ldcg(ge_d + (t - P.cap_e)); }
+                }
                 const int x = pc & 1023, y = (pc >> 10) & 1023, z = (pc >> 20) & 15;
                 const bool alongx = s_pref[z] == 0;
                 const int sgn = (j & 1) ? -1 : 1;
@@ -504,8 +630,9 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 push(won && fv <= B2, (uint32_t)(xv | (yv << 10) | (zv << 20)) | FR_RAYS_BOTH, fv);
               }
             }
-            fl = __reduce_min_sync(0xFFFFFFFFu, fl);
+            fl = __reduce_min_sync(0xFFFFFFFFu, fl); flf = __reduce_min_sync(0xFFFFFFFFu, flf);
             if (lane == 0 && fl != 0xFFFFFFFFu) atomicMin(&S->fmin[nxt], fl);
+            if (WIDE && lane == 0 && flf != 0xFFFFFFFFu) atomicMin(&S->far_min[fc], flf);
             cur = nxt; par ^= 1;
         }
         if (S->err) break;
@@ -699,7 +826,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
         if (blockIdx.x == 0) { atomicAdd(&d.dbg[14], tot); atomicAdd(&d.dbg[15], (unsigned long long)n_rounds); }
         unsigned long long *rec = d.dbg + 16 + 8 * (size_t)env;
         rec[0] = tot; rec[1] = (unsigned long long)n_rounds; rec[2] = (unsigned long long)n_expanded; rec[3] = (unsigned long long)cn;
-        rec[4] = (unsigned long long)ph[3]; rec[5] = (unsigned long long)ph[2]; rec[6] = (unsigned long long)n_ap; rec[7] = (unsigned long long)max_open;
+        rec[4] = (unsigned long long)ph[3]; rec[5] = (unsigned long long)ph[2]; rec[6] = (unsigned long long)ph[7] | ((unsigned long long)n_refill << 40); rec[7] = (unsigned long long)max_open;
     }
 #endif
     if (tid == 0) {
@@ -718,14 +845,17 @@ size_t xr_frontier_smem(const Geo &g, const FrParams &P) {
                4 * XR_ZMAX * 2 + 4 + 3 * XR_ZMAX + 4096 + FR_MAXAP + FR_MAXAP / 2 + FR_MAXAP / 4 + FR_MAXAP / 4;
     return w * 4;
 }
-size_t xr_frontier_spill_words(const FrParams &P) { return 4 * (size_t)P.cap_g + 4 * (size_t)P.cap_ge; }
+size_t xr_frontier_spill_words(const FrParams &P) { return 8 * (size_t)P.cap_g + 4 * (size_t)P.cap_ge; }
 
 cudaError_t xr_frontier_init(int smem_cap) {
-    return cudaFuncSetAttribute(k_route_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+    cudaError_t e = cudaFuncSetAttribute(k_route_frontier<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_route_frontier<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
 }
 
 cudaError_t xr_frontier_launch(const Geo &g, const Dev &d, const int *env_list, int n_envs, const FrParams &P,
                                int threads, cudaStream_t st) {
-    k_route_frontier<<<n_envs, threads, xr_frontier_smem(g, P), st>>>(g, d, env_list, P);
+    if (P.park_min > 0) k_route_frontier<true><<<n_envs, threads, xr_frontier_smem(g, P), st>>>(g, d, env_list, P);
+    else k_route_frontier<false><<<n_envs, threads, xr_frontier_smem(g, P), st>>>(g, d, env_list, P);
     return cudaGetLastError();
 }

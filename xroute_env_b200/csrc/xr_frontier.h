@@ -20,6 +20,8 @@ struct FrParams {
     uint32_t delta;        // entries with f <= (smallest open f) + delta are expanded in the same round (cost units)
     int ray;               // 1..FR_RAY
     int dmax;              // the bucket may widen to dmax * delta while rounds are nearly empty (1 = fixed width)
+    int park_min;          // open-list size from which entries far above the bucket are parked in a far list (0 = never)
+    uint32_t band;         // the far list takes entries with f > (smallest open f) + band (cost units)
 };
 
 size_t xr_frontier_smem(const Geo &g, const FrParams &P);
