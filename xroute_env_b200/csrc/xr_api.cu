@@ -61,6 +61,8 @@ struct XrEnv {
     int32_t *d_lists = nullptr;         // device [1 + XR_NB*XR_NG][N]
     cudaStream_t gs[XR_NG] = {nullptr, nullptr, nullptr};   // one stream per post-route group
     cudaEvent_t ev_fork = nullptr, ev_join[XR_NG] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_glob = nullptr;      // the full-grid sweeps of a step run here, beside the frontier / window kernels
+    cudaEvent_t ev_glob = nullptr;      // ... from the moment the prologue of their environments is done
     int grp_pins[XR_NG] = {0, 4, 8};    // group g = nets with at least grp_pins[g] pins (light / medium / heavy)
     int heavy_cluster = 8;              // minimum cluster size of the heaviest group (0 = same as the others)
     int dual_pins = 8;                  // nets with at least this many pins use the dual cyclic layout (0 = never)
@@ -178,6 +180,8 @@ static void xr_free(XrEnv *env) {
 
     for (int k = 0; k < XR_NG; k++) { if (env->gs[k]) cudaStreamDestroy(env->gs[k]); if (env->ev_join[k]) cudaEventDestroy(env->ev_join[k]); }
     if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+    if (env->s_glob) cudaStreamDestroy(env->s_glob);
+    if (env->ev_glob) cudaEventDestroy(env->ev_glob);
     if (env->ev_done) cudaEventDestroy(env->ev_done);
     for (auto &p : env->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : env->ev_pool) cudaEventDestroy(e);
@@ -373,6 +377,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
         cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
+    cudaStreamCreateWithPriority(&env->s_glob, cudaStreamNonBlocking, prio_hi);
+    cudaEventCreateWithFlags(&env->ev_glob, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&env->ev_done, cudaEventDisableTiming);
     g.guide_cost = std::max(0, cfg->guide_cost); g.halo = std::max(0, std::min(8, cfg->halo));
     env->g.guide_cap = 0;
@@ -920,6 +926,7 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
         if (any_global) { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1, 0); }
         { Launch L(env, XR_K_MISC, st); k_seed<<<g.N, 64, 0, st>>>(env->g, env->d, -1); }
         CK(cudaGetLastError());
+        if (any_global) CK(cudaEventRecord(env->ev_glob, st));
     }
     if (split) CK(cudaEventRecord(env->ev_fork, st));
     for (int gi = 0; gi < XR_NG; gi++) {
@@ -932,6 +939,7 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
             CK(cudaStreamWaitEvent(sg, env->ev_fork, 0));
             if (n_glob[grp]) { Launch L(env, XR_K_ROUTE_BEGIN, sg); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, sg>>>(env->g, env->d, grp, 0); }
             { Launch L(env, XR_K_MISC, sg); k_seed<<<g.N, 64, 0, sg>>>(env->g, env->d, grp); }
+            if (n_glob[grp]) CK(cudaEventRecord(env->ev_glob, sg));       // (only the heaviest group holds full-grid nets)
         }
         if (grp == fr_grp && n_fr) {
             const bool big = n_fr <= env->n_sm;
@@ -960,7 +968,7 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
     env->cur_grp = -1;
     // ---- the results ride on the same read-back as the flags, so xr_step_results needs no second round trip
     env->res_on_host = false;
-    if (any_route && !any_global)
+    if (any_route)
         CK(cudaMemcpyAsync(env->p_res, env->d.cum, env->rb_bytes, cudaMemcpyDeviceToHost, st));   // cum | delta | flags | done
     CK(cudaEventRecord(env->ev_done, st));
     env->pend.active = true; env->pend.any_route = any_route; env->pend.any_global = any_global; env->pend.any_win = any_win;
@@ -986,47 +994,56 @@ extern "C" int xr_step_wait(XrEnv *env) {
     cudaStream_t st = env->pend.st;
     cudaSetDevice(env->device);
     env->pend.active = false;
-    CK(cudaEventSynchronize(env->ev_done)); env->n_sync++;
-    // ---- environments whose window search escaped, or whose window does not fit on chip,
-    // are routed by the full-grid sweeps and finalised in a last pass
-    bool need_global = env->pend.any_global;
-    if (env->pend.any_route && !need_global) {
-        memcpy(env->p_flags, env->p_res + sizeof(int64_t) * XR_M_COUNT * g.N + sizeof(int32_t) * 3 * g.N, sizeof(int32_t) * 2);
-        if (env->p_flags[1] != 0) {
-            const int code = env->p_flags[1];
-            cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
-            return step_failed(env, code);
-        }
-        if (env->p_flags[0] > 0) need_global = true;
-        else env->res_on_host = true;
-    }
-    if (need_global) {
-        // lazy prologue of the environments a window kernel handed over (they skipped k_route_begin): cost flags and
-        // distance field over the whole grid, then the sources / the tree committed so far.  Both kernels return at
-        // once for everybody else.
-        if (env->pend.any_win) {
-            { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1, 1); }
-            { Launch L(env, XR_K_MISC, st); k_handover_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
-        }
+    // ---- full-grid sweeps, pumped from the host until every armed environment is done (flags[0] = armed environments)
+    auto pump = [&](cudaStream_t sp) -> int {
         long long pumps = 0;
         const long long guard = 64ll * (g.X + g.Y + g.Z) + 4096;
         for (;;) {
             for (int p = 0; p < env->pumps_per_sync; p++) {
-                launch_sweep_xz(env, st);
-                launch_sweep_y(env, st);
-                { Launch L(env, XR_K_CONTROL, st); k_control<<<g.N, 32, 0, st>>>(env->g, env->d); }
+                launch_sweep_xz(env, sp);
+                launch_sweep_y(env, sp);
+                { Launch L(env, XR_K_CONTROL, sp); k_control<<<g.N, 32, 0, sp>>>(env->g, env->d); }
             }
             pumps += env->pumps_per_sync;
-            CK(cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st)); env->n_sync++;
-            if (env->p_flags[1] != 0) {
-                const int code = env->p_flags[1];
-                cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
-                return step_failed(env, code);
-            }
-            if (env->p_flags[0] == 0) break;
-            if (pumps > guard * 64) return step_failed(env, 2);
+            if (cudaMemcpyAsync(env->p_flags, env->d.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, sp) != cudaSuccess ||
+                cudaStreamSynchronize(sp) != cudaSuccess) return -1;
+            env->n_sync++;
+            if (env->p_flags[1] != 0) return env->p_flags[1];
+            if (env->p_flags[0] == 0) return 0;
+            if (pumps > guard * 64) return 2;
         }
+    };
+    // Nets known to need the full grid (no window fits a cluster) are pumped on their own stream while the frontier and
+    // window kernels of the other environments are still running: the sweeps are a chain of short dependent launches
+    // that leaves most of the GPU idle.  Environments are independent; a window kernel that hands over meanwhile parks
+    // its environment in phase 2, which the pumps do not touch.
+    int code = 0;
+    if (env->pend.any_global) {
+        CK(cudaStreamWaitEvent(env->s_glob, env->ev_glob, 0));
+        code = pump(env->s_glob);
+    }
+    CK(cudaEventSynchronize(env->ev_done)); env->n_sync++;
+    bool handover = false;
+    if (code == 0 && env->pend.any_route) {
+        const int32_t *fl = reinterpret_cast<const int32_t *>(env->p_res + sizeof(int64_t) * XR_M_COUNT * g.N + sizeof(int32_t) * 3 * g.N);
+        if (fl[1] != 0) code = fl[1];
+        handover = fl[3] > 0;
+    }
+    if (code == 0 && handover) {
+        // lazy prologue of the environments a window kernel handed over (they skipped k_route_begin): cost flags and
+        // distance field over the whole grid, then the sources / the tree committed so far (which arms them).  Both
+        // kernels return at once for everybody else.
+        { Launch L(env, XR_K_ROUTE_BEGIN, st); k_route_begin<<<dim3(grid_cells(g, 4), g.N), 256, 0, st>>>(env->g, env->d, -1, 1); }
+        { Launch L(env, XR_K_MISC, st); k_handover_seed<<<g.N, 64, 0, st>>>(env->g, env->d); }
+        code = pump(st);
+    }
+    if (code != 0) {
+        if (code < 0) return fail(env, XR_E_CUDA, "full-grid sweeps: CUDA error");
+        cudaMemsetAsync(env->d.flags, 0, sizeof(int32_t) * 4, st);
+        return step_failed(env, code);
+    }
+    if (!env->pend.any_global && !handover) env->res_on_host = env->pend.any_route;
+    else {
         if (env->metrics_mode == 1) { Launch L(env, XR_K_METRICS, st); k_metrics<<<dim3(grid_cells(g, 16), g.N), 256, 0, st>>>(env->g, env->d, -1); }
         { Launch L(env, XR_K_MISC, st); k_finalize<<<(g.N + 127) / 128, 128, 0, st>>>(env->g, env->d, -1, env->metrics_mode == 0); }
         {

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp, int 
     const int env = blockIdx.y;
     const int net = d.act[2 * env + 1];
     if (net == 0) return;
-    if (handover) { if (d.mode[env] != 1 || d.phase[env] != 1) return; }
+    if (handover) { if (d.mode[env] != 1 || d.phase[env] != 2) return; }
     else if (d.mode[env] == 1 || (grp >= 0 && d.grp[env] != grp)) return;  // grp >= 0: only this post-route group
     const size_t eoff = (size_t)env * g.cells_p;
     const int n4 = g.cells_p >> 2;
@@ -67,8 +67,10 @@ __global__ void __launch_bounds__(256) k_route_begin(Geo g, Dev d, int grp, int 
 __global__ void k_handover_seed(Geo g, Dev d) {
     const int env = blockIdx.x;
     const int net = d.act[2 * env + 1];
-    if (net == 0 || d.mode[env] != 1 || d.phase[env] != 1) return;
+    if (net == 0 || d.mode[env] != 1 || d.phase[env] != 2) return;
     const size_t eoff = (size_t)env * g.cells_p;
+    __syncthreads();                                      // (everyone has read the phase)
+    if (threadIdx.x == 0) { d.phase[env] = 1; atomicAdd(&d.flags[0], 1); atomicSub(&d.flags[3], 1); }   // armed: the pumps take it from here
     if (d.first[env]) {
         const int *ns = d.net_start + (size_t)env * (g.max_nets + 2);
         const unsigned srcpin = d.net_srcpin[(size_t)env * (g.max_nets + 1) + net];

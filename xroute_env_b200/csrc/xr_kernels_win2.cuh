@@ -607,15 +607,15 @@ __global__ void __launch_bounds__(WIN_T, 1) k_route_win2(Geo g, Dev d, const int
             for (int r = 0; r < C; r++) tot |= *cluster.map_shared_rank(&s_flag[2], r);
             if (tot) {
                 if (rank == 0 && tid == 0) {
-                    d.phase[env] = 1; d.changed[env] = 1; d.reinit[env] = first ? 0 : 1; d.first[env] = first ? 1 : 0;
-                    atomicAdd(&d.flags[0], 1); atomicAdd(&d.flags[2], 1);
+                    d.phase[env] = 2; d.changed[env] = 1; d.reinit[env] = first ? 0 : 1; d.first[env] = first ? 1 : 0;
+                    atomicAdd(&d.flags[3], 1); atomicAdd(&d.flags[2], 1);
                 }
                 break;
             }
         } else if (esc_any) {
             if (tid == 0) {
-                d.phase[env] = 1; d.changed[env] = 1; d.reinit[env] = first ? 0 : 1; d.first[env] = first ? 1 : 0;
-                atomicAdd(&d.flags[0], 1); atomicAdd(&d.flags[2], 1);
+                d.phase[env] = 2; d.changed[env] = 1; d.reinit[env] = first ? 0 : 1; d.first[env] = first ? 1 : 0;
+                atomicAdd(&d.flags[3], 1); atomicAdd(&d.flags[2], 1);
             }
             break;
         }
