@@ -93,6 +93,30 @@ def test_frontier_engine_knobs(knobs, monkeypatch):
     _run_episode(geom, make_batch(geom, 3, 8, seed=901), seed=10, check_obs_every=4)
 
 
+@pytest.mark.parametrize("metrics_mode", [0, 1])
+def test_sweeps_beside_frontier_one_step(metrics_mode, monkeypatch):
+    """One step that uses every route path at once: nets on the frontier kernel, nets on window clusters (some of which
+    escape their window and are handed over), and nets whose window fits no cluster (XR_WIN_FIT_CAP shrinks the fit
+    limit) -- those are pumped by the full-grid sweeps on their own stream while the other kernels run
+    (xr_step_wait).  Bit-exact against the oracle, with both metric modes."""
+    monkeypatch.setenv("XR_HYBRID_AREA", "30")
+    monkeypatch.setenv("XR_HYBRID_PINS", "30")
+    monkeypatch.setenv("XR_WIN_FIT_CAP", "9000")
+    geom = ispd18_geometry(90, 70, 9)
+    insts = make_batch(geom, 12, 10, seed=4100, p_obstacle=0.15, max_degree=5)
+    from xroute_env_b200 import VecGame
+    vg = VecGame(geom, insts, device=0, window_margin=1)
+    vg.reset()
+    rng = np.random.default_rng(3)
+    orders = [list(rng.permutation(i.net_ids)) for i in insts]
+    for t in range(10):
+        vg.step(np.array([int(o[t]) for o in orders], np.int32))
+    c = vg.route_counters()
+    vg.close()
+    assert c["frontier_nets"] > 0 and c["window_nets"] > 0 and c["global_nets"] > 0 and c["window_fallbacks"] > 0, c
+    _run_episode(geom, insts, seed=3, window_margin=1, metrics_mode=metrics_mode, check_obs_every=3)
+
+
 def _with_guides(geom, insts, margin, layers):
     """Synthetic route guides: per net the bounding box of its access points grown by `margin` cells, on `layers`."""
     out = []

@@ -59,6 +59,10 @@ while time.time() - t0 < budget and not bad:
              "XR_FR_DMAX": str(int(rng.choice([1, 4, 16]))), "XR_FR_THREADS": str(int(rng.choice([64, 256, 1024]))),
              "XR_HYBRID_AREA": str(int(rng.choice([0, 30, 400, 4000]))), "XR_HYBRID_PINS": str(int(rng.choice([2, 3, 30]))),
              "XR_FR_PARK": str(int(rng.choice([0, 1, 16, 256, 4096]))), "XR_FR_BAND": str(int(rng.choice([1, 2, 4, 64])))}
+    if rng.random() < 0.4:
+        knobs["XR_WIN_FIT_CAP"] = str(int(rng.choice([3000, 9000, 30000])))
+    else:
+        os.environ.pop("XR_WIN_FIT_CAP", None)
     if rng.random() < 0.3:
         knobs["XR_FR_CAP"] = "64"
     else:

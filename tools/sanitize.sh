@@ -33,3 +33,5 @@ run() { compute-sanitizer --tool $TOOL --error-exitcode 9 python /tmp/san.py 2>&
 echo "== default knobs"; run
 echo "== frontier lists forced through their global spill, 64-thread blocks, short rays"; XR_FR_CAP=64 XR_FR_THREADS=64 XR_FR_RAY=3 run
 echo "== every sweep-engine net through the dual cyclic layout kernel"; XR_DUAL_PINS=2 XR_DUAL_MINC=2 run
+echo "== wide variant of the frontier kernel: far list from the first open entry on"; XR_FR_PARK=1 XR_FR_BAND=1 run
+echo "== hybrid: wide nets on the sweep kernels beside the frontier kernel"; XR_HYBRID_AREA=30 XR_HYBRID_PINS=30 run

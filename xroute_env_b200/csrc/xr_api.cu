@@ -56,6 +56,7 @@ struct XrEnv {
     int pumps_per_sync = 4;
     // window-resident route kernel
     int win_margin = 14, min_cluster = 0, smem_cap = 0, n_sm = 148;
+    int win_fit_cap = 0;                // bytes of shared memory a window may take per CTA (smem_cap; XR_WIN_FIT_CAP lowers it: tests)
     std::vector<int32_t> h_netwin;      // [N][max_nets+1][2]  WX, WY  (0 = no window)
     int32_t *p_lists = nullptr;         // pinned [3 + XR_NB*XR_NG][N]: mode, group, frontier list, env lists of the XR_NG x XR_NB cluster buckets
     int32_t *d_lists = nullptr;         // device [1 + XR_NB*XR_NG][N]
@@ -393,6 +394,8 @@ extern "C" int xr_create(const XrConfig *cfg, XrEnv **out) {
     if (const char *e = getenv("XR_HYBRID_AREA")) if (g.guide_cost == 0 && g.halo == 0) env->hybrid_area = std::max(0, atoi(e));
     if (const char *e = getenv("XR_HYBRID_PINS")) env->hybrid_pins = std::max(2, atoi(e));
     if (const char *e = getenv("XR_METRICS_MODE")) env->metrics_mode = atoi(e) == 1 ? 1 : 0;
+    env->win_fit_cap = env->smem_cap;
+    if (const char *e = getenv("XR_WIN_FIT_CAP")) env->win_fit_cap = std::min(env->smem_cap, std::max(0, atoi(e)));
     ce = xr_frontier_init(env->smem_cap);
     if (ce != cudaSuccess) { std::string m = std::string("frontier kernel attribute: ") + cudaGetErrorString(ce); xr_free(env); return fail(nullptr, XR_E_CUDA, m); }
     // tuning knobs (not part of the ABI): XR_HEAVY_PINS, XR_HEAVY_CLUSTER
@@ -853,7 +856,7 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
                     for (int b = 0; b < NB_BAND && !fits; b++) {
                         if (CS[b] < mc) continue;
                         const int H = (WY + CS[b] - 1) / CS[b];
-                        fits = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX)) <= env->smem_cap;
+                        fits = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX)) <= env->win_fit_cap;
                     }
                     wide = fits;
                 }
@@ -872,7 +875,7 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
                 for (int b = NB_BAND; b < XR_NB && bucket < 0; b++) {
                     if (CS[b] < mc || CS[b] < env->dual_minc) continue;
                     const long long bytes = 4ll * ((long long)WIN2_CELL_WORDS(g.Z, CS[b], WX, WY) + WIN2_AUX_WORDS(g.Z, CS[b], WX, WY));
-                    if (bytes <= env->smem_cap) bucket = b;
+                    if (bytes <= env->win_fit_cap) bucket = b;
                 }
             }
             if (WX > 0 && bucket < 0 && WX < 1024 && WY < 1024 &&          // (the window kernels cache the net's access
@@ -881,7 +884,7 @@ extern "C" int xr_step_async(XrEnv *env, const int32_t *actions, void *stream) {
                     if (CS[b] < mc) continue;
                     const int H = (WY + CS[b] - 1) / CS[b];
                     const long long bytes = 4ll * ((long long)g.Z * (H + 2) * (WX | 1) + WIN_AUX_WORDS(g.Z, H, WX));
-                    if (bytes <= env->smem_cap) bucket = b;
+                    if (bytes <= env->win_fit_cap) bucket = b;
                 }
             }
             for (int k = 1; k < XR_NG; k++) if (np >= env->grp_pins[k]) grp = k;

@@ -15,7 +15,11 @@
 // pass < 0: everything still pending (after the full-grid route loop).  Tag = pass + 2 / 1.
 __device__ __forceinline__ bool pass_selects(const Dev &d, int env, int pass) {
     if (d.fin[env] != 0) return false;
-    return pass < 0 || (d.grp[env] == pass && d.phase[env] == 0);
+    if (pass < 0) return true;
+    // (a net on the full-grid path is pumped on its own stream beside the group passes: it may complete at any moment,
+    // so it always waits for the last pass)
+    if (d.grp[env] != pass || (d.mode[env] == 0 && d.act[2 * env + 1] != 0)) return false;
+    return d.phase[env] == 0;
 }
 __device__ __forceinline__ int pass_tag(int pass) { return pass < 0 ? 1 : pass + 2; }
 
