@@ -546,12 +546,16 @@ def run_ours(args):
         fr = facts.get("k_route_frontier", {})
         n_route_launch = sum(kern[k]["launches"] for k in kern if k.startswith("route") or k.startswith("sweep"))
         roofline.update({
-            "kernel": f"{'k_route_frontier' if dom == 'route_frontier' else dom} (dominant: {sum(kern[k]['share'] for k in kern if k.startswith('route') or k.startswith('sweep')):.3f} "
-                      "of the kernel time of the profiled leg, all route kernels)",
+            "kernel": f"route kernels ({sum(kern[k]['share'] for k in kern if k.startswith('route') or k.startswith('sweep')):.3f} of the kernel time of the "
+                      f"profiled leg; largest share: {'k_route_frontier' if dom == 'route_frontier' else 'k_' + dom}).  k_route_frontier is one launch per step and the step's "
+                      "critical path; the window kernels (k_route_win<C>, hybrid policy) run beside it on their own streams, so kernel-time shares add up to more "
+                      "than the step",
+            "shares": {('k_' + k): kern[k]["share"] for k in kern if k.startswith("route") or k.startswith("sweep")},
+            "avg_launch_us_by_kernel": {('k_' + k): kern[k]["avg_us"] for k in kern if k.startswith("route") or k.startswith("sweep")},
             "bound": "hbm", "achieved": round(alg / (route_ms / 1e3) / 1e9, 2), "frac": round(alg / (route_ms / 1e3) / 1e9 / peak, 5),
             "algorithmic_bytes_per_launch": alg / max(1, n_route_launch), "avg_launch_us": round(1e3 * route_ms / max(1, n_route_launch), 2),
             "traffic": fr.get("dram_bytes_per_launch"),
-            "traffic_source": fr.get("source"),
+            "traffic_source": (fr.get("source") or "") + " -- one k_route_frontier launch; the window kernels work on chip (DRAM throughput ~0, profiles/r1i_ncu_full_route_win2.txt)",
             "efficiency": {"cells_relaxed_per_s": prof_cells / (route_ms / 1e3), "of_5.44e11_cells_per_s": prof_cells / (route_ms / 1e3) / 5.44e11,
                            "issue_slots_busy_pct": fr.get("issue_slots_busy_pct"), "sm_busy_pct": fr.get("sm_busy_pct"),
                            "ctas": fr.get("grid"), "threads_per_cta": fr.get("block"), "registers": fr.get("registers"),
