@@ -154,8 +154,10 @@ int xr_reset(XrEnv *env, const int32_t *env_ids, int32_t k, void *stream);
  *                  read-back of its results on `stream`; it never blocks on the device.  The actions array may be reused
  *                  as soon as it returns.  One step may be in flight per handle (XR_E_STATE otherwise).
  *   xr_step_wait   blocks until that step is complete (one event wait) and reports device-side errors.  Nets whose
- *                  search must run on the full-grid sweeps (engine 1 only, or nets too large for the on-chip tables)
- *                  are finished here: that loop polls a device flag every `pumps_per_sync` iterations.
+ *                  search must run on the full-grid sweeps (windows that fit no cluster of CTAs, nets too large for the
+ *                  on-chip tables, window searches that escaped) are finished here: that loop polls a device flag
+ *                  every `pumps_per_sync` iterations, on a stream of the handle's own while the other kernels of the
+ *                  step are still running.
  *   xr_step        = xr_step_async + xr_step_wait.
  * Every other entry point that touches the state (reset, results, exports) completes a pending step first.
  * A step that fails on the device (XR_E_CAPACITY, XR_E_UNROUTABLE) leaves the batch half-stepped: every environment must
