@@ -78,7 +78,7 @@ while time.time() - t0 < budget and not bad:
         acts = np.array([int(o[t]) if t < len(o) else 0 for o in orders], np.int32)
         try:
             vg.step(acts)
-        except Exception as ex:                 # keep the configuration of a failing step for tools/repro_fuzz.py
+        except Exception as ex:                 # keep the configuration of a failing step for tools/repro_fuzz2.py
             import pickle
             os.makedirs("gpurun_out", exist_ok=True)
             with open("gpurun_out/fuzz_fail.pkl", "wb") as fh:

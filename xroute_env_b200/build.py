@@ -22,7 +22,7 @@ def _deps():
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("XR_NVCC_EXTRA", "").split()      # e.g. -DWIN_PHASE_TIMING for tools/diag_route.py
+    extra = os.environ.get("XR_NVCC_EXTRA", "").split()      # e.g. -DFR_TIMING for tools/diag_frontier.py
     os.makedirs(OBJ, exist_ok=True)
     newest = max(os.path.getmtime(d) for d in _deps())
     tag = os.path.join(OBJ, "flags.txt")
