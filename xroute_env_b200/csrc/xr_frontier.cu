@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(FR_T, FR_MINB) k_route_frontier(Geo g, Dev d, 
                 const uint32_t nd = d0 + wgt;
                 const uint32_t Bnow = *(volatile uint32_t *)&S->B;
                 const bool okk = fresh && nd <= Bnow && nd < dval(wv);
-                const unsigned bits = (__ballot_sync(0xFFFFFFFFu, okk) >> (lane & 24)) & 0xFFu;
+                const unsigned bits = (__ballot_sync(0xFFFFFFFFu, okk) >> (lane & ~(FR_RAY - 1))) & ((1u << FR_RAY) - 1u);
                 const int m = __ffs(~bits) - 1;                       // cells of this ray that are lowered (a prefix)
                 const bool low = valid && k < m;
                 work += fresh ? 1 : 0;

@@ -10,7 +10,9 @@
 #ifndef FR_MINB
 #define FR_MINB 1
 #endif
-#define FR_RAY 8           // cells an expansion relaxes along the layer's preferred direction, at most
+#ifndef FR_RAY
+#define FR_RAY 8           // cells an expansion relaxes along the layer's preferred direction, at most (lanes per ray: 4, 8 or 16)
+#endif
 
 struct FrParams {
     int cap_s;             // open-list entries kept in shared memory (per list)
