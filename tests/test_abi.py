@@ -37,6 +37,26 @@ def test_config_struct_layout_matches_header():
     assert XrConfig.x_coords.offset == 40 and XrConfig.via_cost.offset == 80
 
 
+def test_config_struct_fields_agree_in_header_binding_and_integration_doc():
+    """Field names and order of XrConfig: the header, the ctypes binding and the binding INTEGRATION.md prints."""
+    src = open(os.path.join(ROOT, "include", "xroute_b200.h")).read()
+    body = re.search(r"typedef struct XrConfig \{(.*?)\} XrConfig;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    hdr = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = re.sub(r"^(const\s+)?\w+\s*\*?", "", decl, count=1)
+        hdr += [n.strip().lstrip("*") for n in names.split(",")]
+    from xroute_env_b200._lib import XrConfig
+    assert hdr == [f[0] for f in XrConfig._fields_]
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blk = doc[doc.index("class XrConfig(C.Structure)"):]
+    blk = blk[:blk.index("]\n") + 1]
+    assert hdr == re.findall(r'\("(\w+)",', blk)
+
+
 def test_no_oracle_reference_in_product_package():
     """The product path must not route through the CPU oracle."""
     pkg = os.path.join(ROOT, "xroute_env_b200")
