@@ -1,6 +1,6 @@
 """Step time of the bench workload (or another preset) per routing engine -- development tool.
     python tools/quick_bench.py [preset] [n_envs] [n_nets] [episodes] [engines, e.g. 01]"""
-import os, sys, time
+import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -19,7 +19,7 @@ rng = np.random.default_rng(1)
 orders = np.stack([np.concatenate([rng.permutation(i.net_ids) for _ in range(episodes + 1)]) for i in insts], 1).astype(np.int32)
 ref = None
 for eng in engines:
-    vg = VecGame(geom, insts, device=0, engine=eng, obs_max_nets=obs_cap)
+    vg = VecGame(geom, insts, device=0, engine=eng, obs_max_nets=obs_cap, **json.loads(os.environ.get("XR_QB_KW", "{}")))   # e.g. XR_QB_KW='{"window_margin": 22}'
     t = 0
     def episode():
         global t
