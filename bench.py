@@ -544,6 +544,7 @@ def run_ours(args):
         route_ms = sum(kern[k]["ms_total"] for k in kern if k.startswith("route") or k.startswith("sweep"))
         alg = 12.0 * prof_cells
         fr = facts.get("k_route_frontier", {})
+        fw = facts.get("k_route_win", {})
         n_route_launch = sum(kern[k]["launches"] for k in kern if k.startswith("route") or k.startswith("sweep"))
         roofline.update({
             "kernel": f"route kernels ({sum(kern[k]['share'] for k in kern if k.startswith('route') or k.startswith('sweep')):.3f} of the kernel time of the "
@@ -555,7 +556,8 @@ def run_ours(args):
             "bound": "hbm", "achieved": round(alg / (route_ms / 1e3) / 1e9, 2), "frac": round(alg / (route_ms / 1e3) / 1e9 / peak, 5),
             "algorithmic_bytes_per_launch": alg / max(1, n_route_launch), "avg_launch_us": round(1e3 * route_ms / max(1, n_route_launch), 2),
             "traffic": fr.get("dram_bytes_per_launch"),
-            "traffic_source": (fr.get("source") or "") + " -- one k_route_frontier launch; the window kernels work on chip (DRAM throughput ~0, profiles/r1i_ncu_full_route_win2.txt)",
+            "traffic_source": (fr.get("source") or "") + " -- one k_route_frontier launch; window_kernel holds the same facts of one k_route_win<4> launch",
+            "window_kernel": {k: fw.get(k) for k in ("source", "dram_bytes_per_launch", "issue_slots_busy_pct", "sm_busy_pct", "grid", "block", "registers")},
             "efficiency": {"cells_relaxed_per_s": prof_cells / (route_ms / 1e3), "of_5.44e11_cells_per_s": prof_cells / (route_ms / 1e3) / 5.44e11,
                            "issue_slots_busy_pct": fr.get("issue_slots_busy_pct"), "sm_busy_pct": fr.get("sm_busy_pct"),
                            "ctas": fr.get("grid"), "threads_per_cta": fr.get("block"), "registers": fr.get("registers"),
