@@ -97,5 +97,5 @@ class BatchedRepresentationNetwork(nn.Module):
         rep = obs.new_zeros((N, max_nets, ob.shape[1]))
         for s in range(0, idx.shape[0], chunk):
             e, r = idx[s:s + chunk, 0], idx[s:s + chunk, 1]
-            rep[e, r] = self.encode_nets(nets[e, r])
+            rep[e, r] = self.encode_nets(nets[e, r]).to(rep.dtype)      # (under autocast the tower returns bf16)
         return ob, rep, valid
